@@ -1,0 +1,220 @@
+/*
+ * strawboat_b200.h -- C ABI of the B200-native strawboat page encode/decode backend.
+ *
+ * This is the drop-in boundary for ONE hot path of sundy-li/strawboat: page bytes <-> Arrow
+ * buffers (src/compression + the decompress-into-Arrow half of src/read + the per-page half
+ * of src/write).  Every entry point names the reference interface it replaces (paths are
+ * relative to the reference repo root).  Plain pointers and sizes only; no torch, no C++
+ * types.  The shared library is strawboat_b200/csrc/libstrawboat_b200.so (sm_100a SASS).
+ *
+ * There is NO CPU fallback: every compute entry point fails with SB_CUDA when no usable
+ * CUDA device is present.
+ */
+#ifndef STRAWBOAT_B200_H
+#define STRAWBOAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status: arrow::error::Error variants used on the path (src/errors.rs:19-31,
+ *      src/compression/mod.rs:78-80, src/compression/basic.rs:104,116) ---------------- */
+enum {
+  SB_OK = 0,
+  SB_OUT_OF_SPEC = 1, /* Error::OutOfSpec */
+  SB_IO = 2,          /* Error::Io (short read: "failed to fill whole buffer") */
+  SB_EXTERNAL = 3,    /* Error::External (LZ4 block corrupt) */
+  SB_NYI = 4,         /* Error::NotYetImplemented (zstd / snappy pages, f16, ...) */
+  SB_CUDA = 5,        /* CUDA runtime failure or no device */
+  SB_INVALID_ARG = 6,
+  SB_PANIC = 7,       /* input on which the reference panics (unwrap / assert / OOB slice) */
+};
+
+/* ---- physical leaf types: arrow2 PhysicalType as dispatched by
+ *      src/write/serialize.rs:52-132 and src/read/deserialize.rs:100-138.
+ *      Utf8 is handled as Binary, LargeUtf8 as LargeBinary (serialize.rs:99-105). -------- */
+enum {
+  SB_NULL = 0,
+  SB_BOOL = 1,
+  SB_I8 = 2,
+  SB_I16 = 3,
+  SB_I32 = 4,
+  SB_I64 = 5,
+  SB_U8 = 6,
+  SB_U16 = 7,
+  SB_U32 = 8,
+  SB_U64 = 9,
+  SB_F32 = 10,
+  SB_F64 = 11,
+  SB_BINARY = 12,       /* i32 offsets */
+  SB_LARGE_BINARY = 13, /* i64 offsets */
+};
+
+/* ---- codec ids: src/compression/mod.rs:37-108 --------------------------------------- */
+enum {
+  SB_C_NONE = 0,
+  SB_C_LZ4 = 1,
+  SB_C_ZSTD = 2,
+  SB_C_SNAPPY = 3,
+  SB_C_RLE = 10,
+  SB_C_DICT = 11,
+  SB_C_ONEVALUE = 12,
+  SB_C_FREQ = 13,
+  SB_C_BITPACK = 14,
+  SB_C_DELTABP = 15,
+  SB_C_PATAS = 16,
+};
+
+enum { SB_MEM_HOST = 0, SB_MEM_DEVICE = 1 };
+
+/* arrow2 InitNested, root -> leaf (src/read/deserialize.rs:154-221) */
+enum { SB_N_PRIMITIVE = 0, SB_N_LIST = 1, SB_N_STRUCT = 2 };
+#define SB_MAX_NESTED 8
+
+/* PageMeta (src/lib.rs:71-80): length = encoded bytes of the page, num_values = rows
+ * (flat) or level entries (nested, src/write/common.rs:103). */
+typedef struct {
+  uint64_t length;
+  uint64_t num_values;
+} sb_page_meta;
+
+/* What the reference derives from (Field, ColumnDescriptor, Vec<InitNested>) for one leaf
+ * (src/read/deserialize.rs:100-234). n_nested <= 1 means a flat column. */
+typedef struct {
+  int32_t type;
+  int32_t nullable;
+  int32_t n_nested;
+  int32_t nested_kind[SB_MAX_NESTED];
+  int32_t nested_nullable[SB_MAX_NESTED];
+} sb_leaf;
+
+typedef struct sb_ctx sb_ctx;
+
+/* One context per host thread (the reference's readers/writers are single-threaded objects
+ * with Send+Sync bounds, src/read/deserialize.rs:28).  Owns device scratch pools and a
+ * stream; all work of a call is ordered on that stream and complete on return. */
+int32_t sb_ctx_create(int32_t device, sb_ctx **out);
+void sb_ctx_destroy(sb_ctx *ctx);
+/* Use the caller's CUDA stream (cudaStream_t) instead of the context's own. */
+int32_t sb_ctx_set_stream(sb_ctx *ctx, void *cuda_stream);
+const char *sb_last_error(const sb_ctx *ctx);
+const char *sb_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * DECODE
+ * ------------------------------------------------------------------------------------ */
+
+/* All pages of one leaf column, back to back, exactly as they sit in the file between
+ * ColumnMeta.offset and ColumnMeta.offset + total_len() (src/lib.rs:40-68) -- i.e. what a
+ * NativeReadBuf positioned at the column yields (src/read/mod.rs:26-28). */
+typedef struct {
+  sb_leaf leaf;
+  const uint8_t *bytes;
+  uint64_t nbytes;
+  int32_t mem; /* SB_MEM_HOST or SB_MEM_DEVICE: where `bytes` lives */
+  const sb_page_meta *metas; /* host */
+  uint64_t n_pages;
+} sb_column_in;
+
+/* One decoded Arrow array (the buffers of PrimitiveArray / BooleanArray / BinaryArray /
+ * Utf8Array that src/read/array/{integer,double,boolean,binary}.rs build), plus -- for
+ * nested leaves -- the NestedState of read_validity_nested (src/read/read_basic.rs:65-173).
+ * Pointers are device pointers (out_mem == SB_MEM_DEVICE) or host pointers owned by the
+ * context (SB_MEM_HOST); release with sb_release_columns. */
+typedef struct {
+  uint64_t length;         /* rows (flat) / leaf slots (nested) */
+  void *values;            /* primitives: length*W bytes; bool: bitmap; binary: value bytes */
+  uint64_t values_bytes;
+  void *offsets;           /* binary: (length+1) i32 / i64 */
+  uint64_t offsets_bytes;
+  uint8_t *validity;       /* LSB-first bitmap, NULL when the leaf is not nullable */
+  uint64_t validity_bytes;
+  /* nested leaves only: per depth d < n_nested-1, the entries pushed into NestedState */
+  int64_t *nested_offsets[SB_MAX_NESTED];  /* list start offsets (+ final end offset) */
+  uint8_t *nested_validity[SB_MAX_NESTED]; /* bitmap, NULL if depth not nullable */
+  uint64_t nested_len[SB_MAX_NESTED];      /* entries at that depth */
+  int32_t *page_status;    /* host, n_pages entries: SB_OK or the page's error */
+  int32_t mem;
+  void *_owner;
+} sb_column_out;
+
+/* Replaces read::batch_read::batch_read_array for leaf columns
+ * (src/read/batch_read.rs:190-209 -> read_integer / read_double / read_binary /
+ * read_boolean / read_null, src/read/array/integer.rs:210-238 etc.): decodes every page of
+ * every given column in one batched launch sequence and returns ONE concatenated array per
+ * column.  Returns SB_OK if every page decoded; otherwise the first failing page's status
+ * (per-page detail in page_status; the other pages are still decoded). */
+int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, int32_t out_mem,
+                          sb_column_out *outs);
+
+/* Replaces read::deserialize::column_iter_to_arrays(...).next() / IntegerIter::deserialize
+ * (src/read/deserialize.rs:237-253, src/read/array/integer.rs:68-88): one array PER PAGE.
+ * `pages[i]` is a one-page column (n_pages == 1). Same batching on the device. */
+int32_t sb_decode_pages(sb_ctx *ctx, const sb_column_in *pages, uint64_t n_pages, int32_t out_mem,
+                        sb_column_out *outs);
+
+void sb_release_columns(sb_ctx *ctx, sb_column_out *outs, uint64_t n);
+
+/* Counters of the last decode/encode call on this context. */
+typedef struct {
+  uint64_t pages;
+  uint64_t bytes_in;       /* sum of PageMeta.length */
+  uint64_t bytes_out;      /* Arrow bytes produced (values + offsets + validity) */
+  uint64_t kernel_launches;
+  float device_ms;         /* CUDA-event time of the kernels of the last call */
+  uint64_t codec_pages[32]; /* pages per top-level codec id */
+} sb_stats;
+int32_t sb_last_stats(const sb_ctx *ctx, sb_stats *out);
+
+/* ------------------------------------------------------------------------------------
+ * ENCODE
+ * ------------------------------------------------------------------------------------ */
+
+/* WriteOptions (src/write/common.rs:37-45) + the explicit stand-ins for the reference's
+ * hidden inputs: the sampler seed (thread_rng, src/compression/integer/mod.rs:316) and the
+ * force-codec switch (debug env vars, src/util/env.rs:20-24). */
+typedef struct {
+  int32_t default_compression;   /* SB_C_NONE / SB_C_LZ4 (zstd, snappy: SB_NYI) */
+  double default_compress_ratio; /* < 0 => None: adaptive compression off */
+  uint64_t max_page_size;        /* rows per page; 0 => None: one page per column */
+  uint32_t forbidden_mask;       /* bit c => Compression id c in forbidden_compressions */
+  int32_t force_codec;           /* -1 or a codec id, honoured where applicable */
+  uint64_t seed;                 /* page p of a column samples with seed + p */
+} sb_write_options;
+
+/* One leaf array (what to_leaves yields, src/write/common.rs:68). */
+typedef struct {
+  sb_leaf leaf;
+  uint64_t length;
+  const void *values;          /* primitives / bool bitmap (bit offset 0) / binary value bytes */
+  uint64_t values_bytes;
+  const void *offsets;         /* binary: length+1 offsets */
+  const uint8_t *validity;     /* may be NULL */
+  int32_t mem;
+} sb_leaf_array;
+
+typedef struct {
+  uint8_t *bytes;              /* encoded pages back to back (the column body in the file) */
+  uint64_t nbytes;
+  sb_page_meta *metas;         /* host, n_pages */
+  uint64_t n_pages;
+  int32_t mem;
+  void *_owner;
+} sb_encoded_column;
+
+/* Replaces the page loop of NativeWriter::encode_chunk for flat leaves
+ * (src/write/common.rs:71-115 -> write::write, src/write/serialize.rs:36-132 ->
+ * compress_integer / compress_double / compress_binary / compress_boolean): slices each
+ * leaf into pages of max_page_size rows, chooses a codec per page as choose_compressor
+ * does, and emits the page bytes plus the PageMeta{length,num_values} the footer needs. */
+int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_cols,
+                          const sb_write_options *opts, int32_t out_mem, sb_encoded_column *outs);
+void sb_release_encoded(sb_ctx *ctx, sb_encoded_column *outs, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

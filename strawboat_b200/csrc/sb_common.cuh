@@ -1,0 +1,273 @@
+// sb_common.cuh -- device-side building blocks shared by the decode and encode kernels.
+//
+// Execution model: one CTA of SB_NT = 128 threads (one warp-group) works on
+// one page at a time.  Page bytes arrive in shared memory through the TMA engine
+// (cp.async.bulk, 1-D, mbarrier completion); everything irregular (byte-unaligned fields,
+// bit unpacking, scans, gathers) happens in shared memory / registers; HBM only sees
+// 16-byte aligned bulk reads and coalesced 16-byte vector stores.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/strawboat_b200.h"
+
+#define SB_NT 128
+#define SB_NWARP (SB_NT / 32)
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------
+// descriptors shared between host and device
+// ------------------------------------------------------------------------------------
+struct PageDesc {
+  const uint8_t *src;  // device pointer to the first byte of the page
+  uint32_t len;        // PageMeta.length
+  uint32_t num_values; // PageMeta.num_values (rows, or level entries for nested leaves)
+  uint32_t col;        // column index
+  uint32_t ordinal;    // page index inside its column
+  uint64_t out_elem;   // first output element (row / leaf slot) of this page in its column
+  uint64_t out_byte;   // binary: first output value byte of this page in its column
+};
+
+struct ColDesc {
+  int32_t type;
+  int32_t nullable;
+  int32_t W;        // value width in bytes (primitives), offset width (binary)
+  int32_t is_float;
+  uint8_t *values;
+  uint8_t *offsets;
+  uint8_t *validity;
+  uint64_t length;  // total elements
+};
+
+struct WorkItem {
+  uint32_t page;
+  uint32_t tile;
+};
+
+// ------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA 1-D bulk copy (SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// order prior generic-proxy accesses to shared memory before subsequent async-proxy (TMA) ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "SB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra SB_DONE;\n\t"
+      "bra SB_WAIT;\n\t"
+      "SB_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; gsrc and smem_dst 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------
+// unaligned little-endian loads through aligned accesses (generic address space: the
+// source is either the TMA-staged page in shared memory or, for oversized pages, global)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_u8(const uint8_t *p) { return *p; }
+__device__ __forceinline__ uint32_t ld_u16u(const uint8_t *p) {
+  if (((uintptr_t)p & 1) == 0) return *reinterpret_cast<const uint16_t *>(p);
+  return uint32_t(p[0]) | (uint32_t(p[1]) << 8);
+}
+__device__ __forceinline__ uint32_t ld_u32u(const uint8_t *p) {
+  uint32_t a = uint32_t((uintptr_t)p & 3);
+  const uint32_t *q = reinterpret_cast<const uint32_t *>(p - a);
+  uint32_t lo = q[0];
+  if (a == 0) return lo;
+  return __funnelshift_r(lo, q[1], a * 8);
+}
+__device__ __forceinline__ uint64_t ld_u64u(const uint8_t *p) {
+  uint32_t a = uint32_t((uintptr_t)p & 3);
+  const uint32_t *q = reinterpret_cast<const uint32_t *>(p - a);
+  uint32_t w0 = q[0], w1 = q[1];
+  if (a == 0) return uint64_t(w0) | (uint64_t(w1) << 32);
+  uint32_t w2 = q[2];
+  return uint64_t(__funnelshift_r(w0, w1, a * 8)) | (uint64_t(__funnelshift_r(w1, w2, a * 8)) << 32);
+}
+// 16 bytes from an arbitrary byte address: two aligned 16-byte loads + funnel shifts.
+// Only touches 16-byte granules that contain at least one requested byte.
+__device__ __forceinline__ uint4 ld_u128u(const uint8_t *p) {
+  uint32_t a = uint32_t((uintptr_t)p & 15);
+  const uint4 *q = reinterpret_cast<const uint4 *>(p - a);
+  uint4 q0 = q[0];
+  if (a == 0) return q0;
+  uint4 q1 = q[1];
+  uint32_t sh = (a & 3) * 8;
+  uint4 r;
+  switch (a >> 2) {
+  case 0:
+    r.x = __funnelshift_r(q0.x, q0.y, sh), r.y = __funnelshift_r(q0.y, q0.z, sh);
+    r.z = __funnelshift_r(q0.z, q0.w, sh), r.w = __funnelshift_r(q0.w, q1.x, sh);
+    break;
+  case 1:
+    r.x = __funnelshift_r(q0.y, q0.z, sh), r.y = __funnelshift_r(q0.z, q0.w, sh);
+    r.z = __funnelshift_r(q0.w, q1.x, sh), r.w = __funnelshift_r(q1.x, q1.y, sh);
+    break;
+  case 2:
+    r.x = __funnelshift_r(q0.z, q0.w, sh), r.y = __funnelshift_r(q0.w, q1.x, sh);
+    r.z = __funnelshift_r(q1.x, q1.y, sh), r.w = __funnelshift_r(q1.y, q1.z, sh);
+    break;
+  default:
+    r.x = __funnelshift_r(q0.w, q1.x, sh), r.y = __funnelshift_r(q1.x, q1.y, sh);
+    r.z = __funnelshift_r(q1.y, q1.z, sh), r.w = __funnelshift_r(q1.z, q1.w, sh);
+    break;
+  }
+  return r;
+}
+
+template <int W> struct Elem;
+template <> struct Elem<1> { using T = uint8_t; };
+template <> struct Elem<2> { using T = uint16_t; };
+template <> struct Elem<4> { using T = uint32_t; };
+template <> struct Elem<8> { using T = uint64_t; };
+
+template <int W> __device__ __forceinline__ typename Elem<W>::T ld_elem_u(const uint8_t *p) {
+  if constexpr (W == 1) return uint8_t(*p);
+  else if constexpr (W == 2) return uint16_t(ld_u16u(p));
+  else if constexpr (W == 4) return ld_u32u(p);
+  else return ld_u64u(p);
+}
+
+// ------------------------------------------------------------------------------------
+// warp / block scans
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= uint32_t(d)) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+// saturating add: sums of run lengths are clamped at `cap` (monotone, associative on
+// non-negative inputs) so hostile run lengths cannot wrap the 32-bit positions.
+__device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b, uint32_t cap) {
+  uint64_t s = uint64_t(a) + uint64_t(b);
+  return s > cap ? cap : uint32_t(s);
+}
+__device__ __forceinline__ uint32_t warp_incl_scan_sat(uint32_t v, uint32_t cap) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= uint32_t(d)) v = sat_add(v, t, cap);
+  }
+  return v;
+}
+
+// Block-wide exclusive scan over SB_NT threads (one value per thread).  `ws` is a
+// shared array of SB_NWARP+1 words.  Returns the exclusive prefix; *total = block sum.
+// Contains two __syncthreads().
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *ws, uint32_t *total) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = warp_incl_scan(v);
+  __syncthreads(); // ws may still be read from a previous call
+  if (lane == 31) ws[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < SB_NWARP; ++w) {
+    uint32_t x = ws[w];
+    if (uint32_t(w) < warp) base += x;
+    tot += x;
+  }
+  *total = tot;
+  return base + inc - v;
+}
+__device__ __forceinline__ uint32_t block_excl_scan_sat(uint32_t v, uint32_t cap, uint32_t *ws, uint32_t *total) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = warp_incl_scan_sat(v, cap);
+  uint32_t exc = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) exc = 0;
+  __syncthreads();
+  if (lane == 31) ws[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < SB_NWARP; ++w) {
+    uint32_t x = ws[w];
+    if (uint32_t(w) < warp) base = sat_add(base, x, cap);
+    tot = sat_add(tot, x, cap);
+  }
+  *total = tot;
+  return sat_add(base, exc, cap);
+}
+
+// ------------------------------------------------------------------------------------
+// scratch arena: a bump allocator over the unused part of the CTA's shared memory, falling
+// back to the CTA slot's global scratch (L2-resident) when an intermediate does not fit.
+// All threads of the CTA hold identical copies (allocation is a uniform computation).
+// ------------------------------------------------------------------------------------
+struct Arena {
+  uint8_t *s_cur, *s_end; // shared
+  uint8_t *g_cur, *g_end; // global
+  __device__ __forceinline__ void *alloc(uint64_t bytes) {
+    bytes = (bytes + 15) & ~uint64_t(15);
+    if (uint64_t(s_end - s_cur) >= bytes) {
+      void *p = s_cur;
+      s_cur += bytes;
+      return p;
+    }
+    if (uint64_t(g_end - g_cur) >= bytes) {
+      void *p = g_cur;
+      g_cur += bytes;
+      return p;
+    }
+    return nullptr;
+  }
+  // shared-only allocation (small hot tables)
+  __device__ __forceinline__ void *alloc_shared(uint64_t bytes) {
+    bytes = (bytes + 15) & ~uint64_t(15);
+    if (uint64_t(s_end - s_cur) >= bytes) {
+      void *p = s_cur;
+      s_cur += bytes;
+      return p;
+    }
+    return nullptr;
+  }
+};
+
+struct Dctx {
+  Arena ar;
+  int *err;          // shared: first error of the page (0 = ok)
+  uint32_t *ws;      // shared: SB_NWARP+1 words of scan workspace
+  int *bcast;        // shared: 4 ints for CTA-wide broadcasts
+  __device__ __forceinline__ void flag(int code) { atomicCAS(err, 0, code); }
+};
+
+} // namespace sb

@@ -1,0 +1,905 @@
+// sb_decode.cuh -- CTA-cooperative decoders for strawboat value blocks.
+//
+// Every routine is executed by all SB_NT threads of the CTA with uniform arguments.
+// `src` is a byte pointer of arbitrary alignment into the staged page (shared memory) or,
+// for oversized pages, into global memory; `dst` is the element-aligned destination: the
+// Arrow values buffer in HBM for the top-level block, or an arena buffer for nested
+// blocks (Dict indices, Freq exceptions).  Routines return false on a uniform failure
+// after flagging cx; data-dependent per-thread problems are flagged and clamped.
+//
+// Layouts follow SURVEY.md Appendix A; each decoder cites the reference function whose
+// output it reproduces bit for bit.
+#pragma once
+#include "sb_common.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------
+// emit: write elements [lo, hi) of an element array through a generator, using 16-byte
+// vector stores for the aligned body.  Gen provides seek(i) and next() (consecutive i).
+// ------------------------------------------------------------------------------------
+template <int W, class Gen> __device__ __forceinline__ void emit(uint8_t *dst, uint32_t lo, uint32_t hi, Gen &g) {
+  using T = typename Elem<W>::T;
+  constexpr uint32_t E = 16 / W;
+  const uint32_t tid = threadIdx.x;
+  if (hi <= lo) return;
+  T *out = reinterpret_cast<T *>(dst);
+  uint32_t mis = uint32_t((16 - ((uintptr_t(dst) + uint64_t(lo) * W) & 15)) & 15) / W;
+  uint32_t head_end = min(hi, lo + mis);
+  for (uint32_t i = lo + tid; i < head_end; i += SB_NT) {
+    g.seek(i);
+    out[i] = g.next();
+  }
+  uint32_t nvec = (hi - head_end) / E;
+  for (uint32_t v = tid; v < nvec; v += SB_NT) {
+    uint32_t i = head_end + v * E;
+    g.seek(i);
+    union {
+      uint4 q;
+      T t[E];
+    } u;
+#pragma unroll
+    for (uint32_t j = 0; j < E; ++j) u.t[j] = g.next();
+    *reinterpret_cast<uint4 *>(dst + uint64_t(i) * W) = u.q;
+  }
+  for (uint32_t i = head_end + nvec * E + tid; i < hi; i += SB_NT) {
+    g.seek(i);
+    out[i] = g.next();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// byte copy, arbitrary source alignment -> destination (basic.rs:67-70 `None`)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_bytes(uint8_t *dst, const uint8_t *src, uint64_t nbytes) {
+  const uint32_t tid = threadIdx.x;
+  uint64_t head = min(nbytes, uint64_t((16 - (uintptr_t(dst) & 15)) & 15));
+  for (uint64_t i = tid; i < head; i += SB_NT) dst[i] = src[i];
+  dst += head;
+  src += head;
+  nbytes -= head;
+  uint64_t nvec = nbytes >> 4;
+  if ((uintptr_t(src) & 15) == 0) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    uint64_t v = tid;
+    for (; v + 3 * SB_NT < nvec; v += 4 * SB_NT) { // 4 independent 16-byte loads in flight
+      uint4 a = s[v], b = s[v + SB_NT], c = s[v + 2 * SB_NT], e = s[v + 3 * SB_NT];
+      d[v] = a, d[v + SB_NT] = b, d[v + 2 * SB_NT] = c, d[v + 3 * SB_NT] = e;
+    }
+    for (; v < nvec; v += SB_NT) d[v] = s[v];
+  } else {
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    uint64_t v = tid;
+    for (; v + SB_NT < nvec; v += 2 * SB_NT) {
+      uint4 a = ld_u128u(src + (v << 4)), b = ld_u128u(src + ((v + SB_NT) << 4));
+      d[v] = a, d[v + SB_NT] = b;
+    }
+    for (; v < nvec; v += SB_NT) d[v] = ld_u128u(src + (v << 4));
+  }
+  for (uint64_t i = (nvec << 4) + tid; i < nbytes; i += SB_NT) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------
+// LZ4 block decode by ONE warp (basic.rs:87-91 -> LZ4_decompress_safe with a known output
+// size).  Token stream is serial; literal and match copies are lane-parallel.  Overlapping
+// matches (offset < length) are resolved as dst[op+i] = dst[op-offset + i % offset], whose
+// sources all precede `op`, so the whole match is one parallel step.
+// Returns 0 or SB_EXTERNAL (uniform across the warp).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int lz4_decode_warp(const uint8_t *src, uint32_t clen, uint8_t *dst, uint32_t dlen) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t ip = 0, op = 0;
+  if (clen == 0) return dlen == 0 ? 0 : SB_EXTERNAL;
+  for (;;) {
+    if (ip >= clen) return SB_EXTERNAL;
+    uint32_t token = src[ip++];
+    uint32_t lit = token >> 4;
+    if (lit == 15) {
+      uint32_t b;
+      do {
+        if (ip >= clen) return SB_EXTERNAL;
+        b = src[ip++];
+        lit += b;
+      } while (b == 255);
+    }
+    if (lit > clen - ip || lit > dlen - op) return SB_EXTERNAL;
+    if (lit) {
+      const uint8_t *s = src + ip;
+      uint8_t *d = dst + op;
+      if (lit >= 256) { // long literal run: vectorise the aligned body
+        uint32_t head = min(lit, uint32_t((16 - (uintptr_t(d) & 15)) & 15));
+        for (uint32_t i = lane; i < head; i += 32) d[i] = s[i];
+        uint32_t nvec = (lit - head) >> 4;
+        for (uint32_t v = lane; v < nvec; v += 32)
+          *reinterpret_cast<uint4 *>(d + head + (v << 4)) = ld_u128u(s + head + (v << 4));
+        for (uint32_t i = head + (nvec << 4) + lane; i < lit; i += 32) d[i] = s[i];
+      } else {
+        for (uint32_t i = lane; i < lit; i += 32) d[i] = s[i];
+      }
+    }
+    ip += lit;
+    op += lit;
+    if (ip == clen) break; // last sequence carries literals only
+    if (clen - ip < 2) return SB_EXTERNAL;
+    uint32_t offset = uint32_t(src[ip]) | (uint32_t(src[ip + 1]) << 8);
+    ip += 2;
+    if (offset == 0 || offset > op) return SB_EXTERNAL;
+    uint32_t ml = token & 15;
+    if (ml == 15) {
+      uint32_t b;
+      do {
+        if (ip >= clen) return SB_EXTERNAL;
+        b = src[ip++];
+        ml += b;
+      } while (b == 255);
+    }
+    ml += 4;
+    if (ml > dlen - op) return SB_EXTERNAL;
+    __syncwarp();
+    {
+      uint8_t *d = dst + op;
+      const uint8_t *m = d - offset;
+      if (offset >= ml) {
+        for (uint32_t i = lane; i < ml; i += 32) d[i] = m[i];
+      } else {
+        for (uint32_t i = lane; i < ml; i += 32) d[i] = m[i % offset];
+      }
+    }
+    op += ml;
+    __syncwarp();
+  }
+  return op == dlen ? 0 : SB_EXTERNAL;
+}
+
+// Basic codecs (CommonCompression::decompress, basic.rs:62-72) into `dst`.
+__device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *src, uint32_t clen, uint8_t *dst,
+                                          uint64_t out_bytes) {
+  if (codec == SB_C_NONE) {
+    if (uint64_t(clen) != out_bytes) { // copy_from_slice length mismatch panics (basic.rs:68)
+      cx.flag(SB_PANIC);
+      return false;
+    }
+    copy_bytes(dst, src, out_bytes);
+    return true;
+  }
+  if (codec == SB_C_LZ4) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int rc = lz4_decode_warp(src, clen, dst, uint32_t(out_bytes));
+      if (threadIdx.x == 0) cx.bcast[0] = rc;
+    }
+    __syncthreads();
+    int rc = cx.bcast[0];
+    if (rc) {
+      cx.flag(rc);
+      return false;
+    }
+    return true;
+  }
+  cx.flag(SB_NYI); // zstd / snappy pages: SURVEY §8 f3
+  return false;
+}
+
+// ------------------------------------------------------------------------------------
+// OneValue (integer/one_value.rs:77-94): payload = one W-byte value
+// ------------------------------------------------------------------------------------
+template <int W> struct GenConst {
+  typename Elem<W>::T v;
+  __device__ __forceinline__ void seek(uint32_t) {}
+  __device__ __forceinline__ typename Elem<W>::T next() { return v; }
+};
+template <int W> __device__ __forceinline__ bool dec_onevalue(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t lo,
+                                                              uint32_t hi, uint8_t *dst) {
+  if (avail < uint32_t(W)) {
+    cx.flag(SB_IO);
+    return false;
+  }
+  GenConst<W> g{ld_elem_u<W>(src)};
+  emit<W>(dst, lo, hi, g);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------
+// RLE (integer/rle.rs:106-134, double/rle.rs:105-135): (u32 run, W-byte value)*
+// Runs are consumed in chunks of SB_NT*8; a block scan turns run lengths into start
+// positions; each output vector binary-searches its first run and then walks forward.
+// ------------------------------------------------------------------------------------
+template <int W> struct GenRle {
+  const uint32_t *starts; // chunk-local run start positions (absolute element index), CH+1 entries
+  const uint8_t *runs;    // first run of the chunk
+  uint32_t nr;            // runs in chunk
+  uint32_t r, i;
+  typename Elem<W>::T cur;
+  __device__ __forceinline__ void seek(uint32_t idx) {
+    uint32_t lo = 0, hi = nr; // largest r with starts[r] <= idx
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (starts[mid] <= idx) lo = mid;
+      else hi = mid;
+    }
+    r = lo;
+    i = idx;
+    cur = ld_elem_u<W>(runs + uint64_t(r) * (4 + W) + 4);
+  }
+  __device__ __forceinline__ typename Elem<W>::T next() {
+    if (i >= starts[r + 1]) {
+      do ++r;
+      while (r + 1 < nr && i >= starts[r + 1]);
+      cur = ld_elem_u<W>(runs + uint64_t(r) * (4 + W) + 4);
+    }
+    ++i;
+    return cur;
+  }
+};
+template <int W> __device__ bool dec_rle(Dctx &cx, const uint8_t *src, uint32_t plen, uint32_t n, uint8_t *dst) {
+  constexpr uint32_t STR = 4 + W, RPT = 8, CH = SB_NT * RPT;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nruns = plen / STR;
+  Arena mark = cx.ar;
+  uint32_t *starts = static_cast<uint32_t *>(cx.ar.alloc((CH + 1) * 4));
+  if (!starts) {
+    cx.flag(SB_NYI);
+    return false;
+  }
+  uint32_t done = 0;
+  for (uint32_t r0 = 0; r0 < nruns && done < n; r0 += CH) {
+    uint32_t lens[RPT], sum = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < RPT; ++j) {
+      uint32_t r = r0 + tid * RPT + j;
+      lens[j] = r < nruns ? min(ld_u32u(src + uint64_t(r) * STR), n) : 0u;
+      sum = sat_add(sum, lens[j], n);
+    }
+    uint32_t total;
+    uint32_t pre = block_excl_scan_sat(sum, n, cx.ws, &total);
+    pre = sat_add(pre, done, n);
+#pragma unroll
+    for (uint32_t j = 0; j < RPT; ++j) {
+      starts[tid * RPT + j] = pre;
+      pre = sat_add(pre, lens[j], n);
+    }
+    uint32_t hi = sat_add(done, total, n);
+    if (tid == 0) starts[CH] = hi;
+    __syncthreads();
+    GenRle<W> g;
+    g.starts = starts;
+    g.runs = src + uint64_t(r0) * STR;
+    g.nr = min(CH, nruns - r0);
+    emit<W>(dst, done, hi, g);
+    done = hi;
+    __syncthreads();
+  }
+  cx.ar = mark;
+  if (done < n) { // read past the runs: "failed to fill whole buffer"
+    cx.flag(SB_IO);
+    return false;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------
+// BitPacker4x blocks (integer/bp.rs:67-86, delta_bp.rs:69-91; layout SURVEY App. D.1):
+// per 128 values `[u8 b][16*b bytes]`; value i = lane i%4, position i/4 of that lane's
+// LSB-first stream; word w of lane l at u32 index 4w+l, i.e. 16-byte rows of 4 lanes.
+// One warp decodes one block: thread t extracts position t of all 4 lanes = the 16-byte
+// output vector out[4t..4t+3].  Every warp walks the (data-dependent) block chain itself.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 bp_unpack_lane(const uint8_t *blk, uint32_t bits, uint32_t t) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (bits == 0) return v;
+  uint32_t bit = t * bits, w = bit >> 5, s = bit & 31;
+  uint4 r0 = ld_u128u(blk + 16 * w);
+  uint4 r1 = make_uint4(0, 0, 0, 0);
+  if (s + bits > 32) r1 = ld_u128u(blk + 16 * (w + 1));
+  uint32_t mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+  v.x = __funnelshift_r(r0.x, r1.x, s) & mask;
+  v.y = __funnelshift_r(r0.y, r1.y, s) & mask;
+  v.z = __funnelshift_r(r0.z, r1.z, s) & mask;
+  v.w = __funnelshift_r(r0.w, r1.w, s) & mask;
+  return v;
+}
+__device__ __forceinline__ void bp_store(uint32_t *dst, uint32_t base, uint32_t n, uint4 v) {
+  if (base + 4 <= n && ((uintptr_t(dst + base) & 15) == 0)) {
+    *reinterpret_cast<uint4 *>(dst + base) = v;
+  } else {
+    if (base < n) dst[base] = v.x;
+    if (base + 1 < n) dst[base + 1] = v.y;
+    if (base + 2 < n) dst[base + 2] = v.z;
+    if (base + 3 < n) dst[base + 3] = v.w;
+  }
+}
+template <bool DELTA> __device__ bool dec_bitpack(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, uint8_t *dst8) {
+  uint32_t *dst = reinterpret_cast<uint32_t *>(dst8);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t nblk = (n + 127) >> 7;
+  Arena mark = cx.ar;
+  uint32_t *blk_pos = nullptr, *blk_sum = nullptr;
+  if (DELTA) {
+    blk_pos = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(nblk) * 4));
+    blk_sum = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(nblk) * 4));
+    if (!blk_pos || !blk_sum) {
+      cx.flag(SB_NYI);
+      return false;
+    }
+  }
+  uint32_t pos = 0;
+  for (uint32_t b = 0; b < nblk; ++b) {
+    if (pos >= avail) {
+      cx.flag(SB_IO);
+      return false;
+    }
+    uint32_t bits = src[pos];
+    if (bits > 32 || 16 * bits > avail - pos - 1) {
+      cx.flag(SB_PANIC);
+      return false;
+    }
+    if ((b & (SB_NWARP - 1)) == warp) {
+      uint4 v = bp_unpack_lane(src + pos + 1, bits, lane);
+      if (!DELTA) {
+        bp_store(dst, b * 128 + lane * 4, n, v);
+      } else {
+        uint32_t s = warp_sum(v.x + v.y + v.z + v.w);
+        if (lane == 0) {
+          blk_pos[b] = pos;
+          blk_sum[b] = s;
+        }
+      }
+    }
+    pos += 1 + 16 * bits;
+  }
+  if (DELTA) {
+    __syncthreads();
+    // exclusive scan of block sums -> `initial` of every block (delta_bp.rs:73,87)
+    uint32_t carry = 0;
+    for (uint32_t b0 = 0; b0 < nblk; b0 += SB_NT) {
+      uint32_t b = b0 + tid;
+      uint32_t v = b < nblk ? blk_sum[b] : 0u, total;
+      uint32_t ex = block_excl_scan(v, cx.ws, &total);
+      if (b < nblk) blk_sum[b] = carry + ex;
+      carry += total;
+    }
+    __syncthreads();
+    for (uint32_t b = warp; b < nblk; b += SB_NWARP) {
+      uint32_t p = blk_pos[b];
+      uint32_t bits = src[p];
+      uint4 v = bp_unpack_lane(src + p + 1, bits, lane);
+      v.y += v.x;
+      v.z += v.y;
+      v.w += v.z;
+      uint32_t inc = warp_incl_scan(v.w);
+      uint32_t base = blk_sum[b] + inc - v.w;
+      v.x += base, v.y += base, v.z += base, v.w += base;
+      bp_store(dst, b * 128 + lane * 4, n, v);
+    }
+  }
+  cx.ar = mark;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------
+// Patas (double/patas.rs:107-132).  Serial variable-length stream; v1: one thread walks it
+// with a 128-entry ring of previous values in shared memory (reference_diff <= 127).
+// ------------------------------------------------------------------------------------
+template <int W> __device__ bool dec_patas(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, uint8_t *dst) {
+  using T = typename Elem<W>::T;
+  Arena mark = cx.ar;
+  uint64_t *ring = static_cast<uint64_t *>(cx.ar.alloc_shared(128 * 8));
+  if (!ring) ring = static_cast<uint64_t *>(cx.ar.alloc(128 * 8));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int rc = 0;
+    if (n == 0) rc = SB_PANIC; // `length - 1` underflows (patas.rs:117)
+    else if (avail < uint32_t(W)) rc = SB_IO;
+    else {
+      T *out = reinterpret_cast<T *>(dst);
+      T first = ld_elem_u<W>(src);
+      out[0] = first;
+      ring[0] = first;
+      uint32_t pos = W;
+      for (uint32_t i = 1; i < n; ++i) {
+        if (avail - pos < 2) {
+          rc = SB_IO;
+          break;
+        }
+        uint32_t p = ld_u16u(src + pos);
+        pos += 2;
+        uint32_t ref = (p >> 9) & 0x7f, sig = (p >> 6) & 7, tz = p & 0x3f;
+        if (tz < 63 && sig == 0) sig = 8; // unpack(), patas.rs:158-160
+        if (sig > uint32_t(W) || avail - pos < sig || ref == 0 || ref > i) { // App. C4 / OOB index panics
+          rc = SB_PANIC;
+          break;
+        }
+        uint64_t val = 0;
+        for (uint32_t b = 0; b < sig; ++b) val |= uint64_t(src[pos + b]) << (8 * b);
+        pos += sig;
+        uint64_t prev = ring[(i - ref) & 127];
+        uint64_t x = (val << tz) ^ prev;
+        if (W == 4) x &= 0xffffffffull;
+        out[i] = T(x);
+        ring[i & 127] = x;
+      }
+    }
+    cx.bcast[0] = rc;
+  }
+  __syncthreads();
+  cx.ar = mark;
+  int rc = cx.bcast[0];
+  if (rc) {
+    cx.flag(rc);
+    return false;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------
+// value-block dispatcher: decompress_integer / decompress_double
+// (integer/mod.rs:72-117, double/mod.rs:69-114).  LEVEL bounds the codec nesting
+// (Dict -> indices, Freq -> exceptions; at most 3 stacked headers).
+// ------------------------------------------------------------------------------------
+template <int LEVEL>
+__device__ bool decode_fixed(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, int W, bool is_float,
+                             uint8_t *dst, uint32_t *consumed);
+
+template <int W> struct GenDict {
+  const uint32_t *idx;
+  const uint8_t *tab; // k entries of W bytes (aligned copy or unaligned in-page)
+  uint32_t k, i;
+  int *err;
+  bool aligned;
+  __device__ __forceinline__ void seek(uint32_t x) { i = x; }
+  __device__ __forceinline__ typename Elem<W>::T next() {
+    uint32_t id = idx[i++];
+    if (id >= k) { // data[*i as usize] out of bounds panics (integer/dict.rs:100)
+      atomicCAS(err, 0, int(SB_PANIC));
+      id = 0;
+    }
+    if (aligned) return reinterpret_cast<const typename Elem<W>::T *>(tab)[id];
+    return ld_elem_u<W>(tab + uint64_t(id) * W);
+  }
+};
+
+// Dict (integer/dict.rs:75-103): [VALUE_BLOCK<u32> indices][u32 k][k * W bytes]
+template <int LEVEL, int W>
+__device__ bool dec_dict(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, uint8_t *dst) {
+  if constexpr (LEVEL >= 2) {
+    cx.flag(SB_OUT_OF_SPEC);
+    return false;
+  } else {
+    Arena mark = cx.ar;
+    uint32_t *idx = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
+    if (!idx) {
+      cx.flag(SB_NYI);
+      return false;
+    }
+    uint32_t used = 0;
+    if (!decode_fixed<LEVEL + 1>(cx, src, avail, n, 4, false, reinterpret_cast<uint8_t *>(idx), &used)) return false;
+    if (avail - used < 4) {
+      cx.flag(SB_IO);
+      return false;
+    }
+    uint32_t k = ld_u32u(src + used);
+    const uint8_t *table = src + used + 4;
+    if (uint64_t(k) * W > uint64_t(avail - used - 4)) { // dict.rs:80-86
+      cx.flag(SB_OUT_OF_SPEC);
+      return false;
+    }
+    GenDict<W> g;
+    g.idx = idx;
+    g.k = k;
+    g.err = cx.err;
+    g.tab = table;
+    g.aligned = (uintptr_t(table) & (W - 1)) == 0;
+    if (!g.aligned) {
+      uint8_t *tab = static_cast<uint8_t *>(cx.ar.alloc_shared(uint64_t(k) * W));
+      if (tab) {
+        copy_bytes(tab, table, uint64_t(k) * W);
+        g.tab = tab;
+        g.aligned = true;
+      }
+    }
+    __syncthreads(); // indices + table visible
+    emit<W>(dst, 0, n, g);
+    cx.ar = mark;
+    return true;
+  }
+}
+
+// Freq (integer/freq.rs:88-123): [W top][u32 bm][roaring][VALUE_BLOCK<T> exceptions]
+// Roaring portable format: array containers scatter directly; bitmap
+// containers rank their bits with a block scan of word popcounts.
+template <int LEVEL, int W>
+__device__ bool dec_freq(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, bool is_float, uint8_t *dst) {
+  using T = typename Elem<W>::T;
+  if constexpr (LEVEL >= 2) {
+    cx.flag(SB_OUT_OF_SPEC);
+    return false;
+  } else {
+    const uint32_t tid = threadIdx.x;
+    if (avail < uint32_t(W) + 4) {
+      cx.flag(SB_IO);
+      return false;
+    }
+    T top = ld_elem_u<W>(src);
+    uint32_t bm = ld_u32u(src + W);
+    const uint8_t *rb = src + W + 4;
+    uint32_t rest = avail - W - 4;
+    if (bm > rest) {
+      cx.flag(SB_PANIC);
+      return false;
+    }
+    // --- roaring header
+    if (bm < 8) {
+      cx.flag(SB_IO);
+      return false;
+    }
+    uint32_t cookie = ld_u32u(rb);
+    if (cookie != 12346u) { // run containers (cookie 12347) are never written by roaring 0.10 serialize_into
+      cx.flag((cookie & 0xffff) == 12347u ? SB_NYI : SB_IO);
+      return false;
+    }
+    uint32_t ncont = ld_u32u(rb + 4);
+    if (ncont > 65536 || uint64_t(ncont) * 8 + 8 > bm) {
+      cx.flag(SB_IO);
+      return false;
+    }
+    // fill with the top value first (freq.rs:99-100)
+    GenConst<W> gc{top};
+    emit<W>(dst, 0, n, gc);
+    // total cardinality and container data offsets (uniform serial walk; ncont = rows/65536)
+    uint32_t n_exc = 0;
+    {
+      uint64_t off = 8 + uint64_t(ncont) * 8, tot = 0;
+      for (uint32_t c = 0; c < ncont; ++c) {
+        uint32_t card = ld_u16u(rb + 8 + 4 * c + 2) + 1;
+        off += card > 4096 ? 8192 : card * 2;
+        tot += card;
+      }
+      if (off > bm || tot > 0xffffffffull) {
+        cx.flag(SB_IO);
+        return false;
+      }
+      n_exc = uint32_t(tot);
+    }
+    Arena mark = cx.ar;
+    T *exc = static_cast<T *>(cx.ar.alloc(uint64_t(n_exc) * W + 16));
+    if (!exc) {
+      cx.flag(SB_NYI);
+      return false;
+    }
+    uint32_t used = 0;
+    if (!decode_fixed<LEVEL + 1>(cx, rb + bm, rest - bm, n_exc, W, is_float, reinterpret_cast<uint8_t *>(exc), &used))
+      return false;
+    __syncthreads(); // fill + exceptions complete before the scatter
+    T *out = reinterpret_cast<T *>(dst);
+    uint32_t rank_base = 0;
+    uint64_t off = 8 + uint64_t(ncont) * 8;
+    for (uint32_t c = 0; c < ncont; ++c) {
+      uint32_t key = ld_u16u(rb + 8 + 4 * c), card = ld_u16u(rb + 8 + 4 * c + 2) + 1;
+      const uint8_t *data = rb + off;
+      if (card <= 4096) {
+        for (uint32_t j = tid; j < card; j += SB_NT) {
+          uint32_t row = (key << 16) | ld_u16u(data + 2 * j);
+          if (row < n) out[row] = exc[rank_base + j];
+          else cx.flag(SB_PANIC); // output[begin + val] out of bounds
+        }
+        off += card * 2;
+      } else {
+        // 1024 u64 words; 8 consecutive words per thread
+        uint64_t wds[8];
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          wds[j] = ld_u64u(data + 8 * (tid * 8 + j));
+          cnt += __popcll(wds[j]);
+        }
+        uint32_t total;
+        uint32_t pre = block_excl_scan(cnt, cx.ws, &total);
+        uint32_t r = rank_base + pre;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint64_t bits = wds[j];
+          while (bits) {
+            uint32_t b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            uint32_t row = (key << 16) | ((tid * 8 + j) * 64 + b);
+            if (row < n && r < n_exc) out[row] = exc[r];
+            else cx.flag(SB_PANIC);
+            ++r;
+          }
+        }
+        off += 8192;
+      }
+      rank_base += card;
+    }
+    cx.ar = mark;
+    return true;
+  }
+}
+
+template <int LEVEL, int W>
+__device__ __forceinline__ bool decode_fixed_w(Dctx &cx, int codec, const uint8_t *body, uint32_t compressed,
+                                               uint32_t body_avail, uint32_t n, bool is_float, uint8_t *dst) {
+  switch (codec) {
+  case SB_C_NONE:
+  case SB_C_LZ4:
+  case SB_C_ZSTD:
+  case SB_C_SNAPPY: return dec_basic(cx, codec, body, compressed, dst, uint64_t(n) * W);
+  case SB_C_RLE: return dec_rle<W>(cx, body, min(compressed, body_avail), n, dst);
+  case SB_C_ONEVALUE: return dec_onevalue<W>(cx, body, body_avail, 0, n, dst);
+  case SB_C_DICT: return dec_dict<LEVEL, W>(cx, body, body_avail, n, dst);
+  case SB_C_FREQ: return dec_freq<LEVEL, W>(cx, body, body_avail, n, is_float, dst);
+  case SB_C_BITPACK:
+  case SB_C_DELTABP:
+    if (is_float) { // double/mod.rs:143-158
+      cx.flag(SB_OUT_OF_SPEC);
+      return false;
+    }
+    if constexpr (W == 4) {
+      return codec == SB_C_BITPACK ? dec_bitpack<false>(cx, body, body_avail, n, dst)
+                                   : dec_bitpack<true>(cx, body, body_avail, n, dst);
+    } else {
+      cx.flag(SB_PANIC); // bp.rs:70-79 writes u32 lanes whatever T is (App. C3)
+      return false;
+    }
+  case SB_C_PATAS:
+    if (!is_float) { // integer/mod.rs:146-161
+      cx.flag(SB_OUT_OF_SPEC);
+      return false;
+    }
+    if constexpr (W == 4 || W == 8) return dec_patas<W>(cx, body, body_avail, n, dst);
+    cx.flag(SB_OUT_OF_SPEC);
+    return false;
+  default: cx.flag(SB_OUT_OF_SPEC); return false; // compression/mod.rs:78-80
+  }
+}
+
+template <int LEVEL>
+__device__ bool decode_fixed(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, int W, bool is_float,
+                             uint8_t *dst, uint32_t *consumed) {
+  if (avail < 9) { // read_compress_header (read_basic.rs:181-189)
+    cx.flag(SB_IO);
+    return false;
+  }
+  int codec = src[0];
+  uint32_t compressed = ld_u32u(src + 1);
+  const uint8_t *body = src + 9;
+  uint32_t body_avail = avail - 9;
+  if (compressed > body_avail) {
+    cx.flag(SB_IO);
+    return false;
+  }
+  *consumed = 9 + compressed;
+  switch (W) {
+  case 1: return decode_fixed_w<LEVEL, 1>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  case 2: return decode_fixed_w<LEVEL, 2>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  case 4: return decode_fixed_w<LEVEL, 4>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  default: return decode_fixed_w<LEVEL, 8>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// bit streams: validity (read_validity, read_basic.rs:36-63) and boolean values
+// (boolean/mod.rs:87-92).  Destination is an LSB-first Arrow bitmap at an arbitrary bit
+// offset (pages are concatenated); it is zero-initialised by the host, whole words are
+// stored, boundary words are OR-merged atomically with the neighbouring pages.
+// ------------------------------------------------------------------------------------
+template <class BitSrc>
+__device__ __forceinline__ void emit_bits(uint8_t *dst_bitmap, uint64_t dst_bit, uint32_t nbits, BitSrc &bs) {
+  if (nbits == 0) return;
+  uint32_t *words = reinterpret_cast<uint32_t *>(dst_bitmap);
+  uint64_t w_first = dst_bit >> 5, w_last = (dst_bit + nbits - 1) >> 5;
+  for (uint64_t w = w_first + threadIdx.x; w <= w_last; w += SB_NT) {
+    int64_t s = int64_t(w << 5) - int64_t(dst_bit); // source bit index of this word's bit 0
+    uint32_t val = bs.word(s, nbits);
+    bool partial = (s < 0) || (uint64_t(s) + 32 > nbits);
+    if (partial) {
+      if (val) atomicOr(words + w, val);
+    } else {
+      words[w] = val;
+    }
+  }
+}
+// 32 source bits starting at (possibly negative) bit s from a packed byte stream of nbits
+struct BitsPacked {
+  const uint8_t *p;
+  __device__ __forceinline__ uint32_t word(int64_t s, uint32_t nbits) const {
+    uint32_t lo_skip = s < 0 ? uint32_t(-s) : 0u; // bits below the stream start
+    uint64_t s0 = s < 0 ? 0 : uint64_t(s);
+    uint32_t want = 32 - lo_skip;                 // bits wanted from s0
+    uint64_t avail = nbits - s0;
+    uint32_t take = avail < want ? uint32_t(avail) : want;
+    uint64_t byte = s0 >> 3;
+    uint32_t sh = uint32_t(s0 & 7);
+    uint32_t nbytes = (sh + take + 7) >> 3; // <= 5
+    uint64_t acc = 0;
+    for (uint32_t b = 0; b < nbytes; ++b) acc |= uint64_t(p[byte + b]) << (8 * b);
+    uint32_t v = uint32_t(acc >> sh);
+    if (take < 32) v &= (1u << take) - 1u;
+    return v << lo_skip;
+  }
+};
+struct BitsConst {
+  bool one;
+  __device__ __forceinline__ uint32_t word(int64_t s, uint32_t nbits) const {
+    if (!one) return 0;
+    uint32_t lo_skip = s < 0 ? uint32_t(-s) : 0u;
+    uint64_t s0 = s < 0 ? 0 : uint64_t(s);
+    uint32_t want = 32 - lo_skip;
+    uint64_t avail = nbits - s0;
+    uint32_t take = avail < want ? uint32_t(avail) : want;
+    uint32_t v = take >= 32 ? 0xffffffffu : ((1u << take) - 1u);
+    return v << lo_skip;
+  }
+};
+
+// boolean RLE (boolean/rle.rs:41-55): (u32 run, u8 0/1)*; expanded per chunk of runs into
+// a shared bit staging buffer, then emitted at the destination bit offset.
+__device__ bool dec_bool_rle(Dctx &cx, const uint8_t *src, uint32_t plen, uint32_t n, uint8_t *dst_bitmap,
+                             uint64_t dst_bit) {
+  constexpr uint32_t STR = 5, RPT = 8, CH = SB_NT * RPT;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nruns = plen / STR;
+  Arena mark = cx.ar;
+  uint32_t *starts = static_cast<uint32_t *>(cx.ar.alloc((CH + 1) * 4));
+  if (!starts) {
+    cx.flag(SB_NYI);
+    return false;
+  }
+  uint32_t *words = reinterpret_cast<uint32_t *>(dst_bitmap);
+  uint32_t done = 0;
+  for (uint32_t r0 = 0; r0 < nruns && done < n; r0 += CH) {
+    uint32_t lens[RPT], sum = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < RPT; ++j) {
+      uint32_t r = r0 + tid * RPT + j;
+      lens[j] = r < nruns ? min(ld_u32u(src + uint64_t(r) * STR), n) : 0u;
+      sum = sat_add(sum, lens[j], n);
+    }
+    uint32_t total;
+    uint32_t pre = sat_add(block_excl_scan_sat(sum, n, cx.ws, &total), done, n);
+#pragma unroll
+    for (uint32_t j = 0; j < RPT; ++j) {
+      starts[tid * RPT + j] = pre;
+      pre = sat_add(pre, lens[j], n);
+    }
+    uint32_t hi = sat_add(done, total, n);
+    if (tid == 0) starts[CH] = hi;
+    __syncthreads();
+    uint32_t nr = min(CH, nruns - r0);
+    if (hi > done) {
+      // output words covering bits [done, hi)
+      uint64_t b0 = dst_bit + done, b1 = dst_bit + hi; // absolute bit range
+      for (uint64_t w = (b0 >> 5) + tid; w <= ((b1 - 1) >> 5); w += SB_NT) {
+        uint64_t wb = w << 5;
+        uint64_t lo_abs = wb < b0 ? b0 : wb, hi_abs = (wb + 32) < b1 ? (wb + 32) : b1;
+        uint32_t e = uint32_t(lo_abs - dst_bit), e_end = uint32_t(hi_abs - dst_bit);
+        uint32_t lo = 0, hh = nr; // largest r with starts[r] <= e
+        while (hh - lo > 1) {
+          uint32_t mid = (lo + hh) >> 1;
+          if (starts[mid] <= e) lo = mid;
+          else hh = mid;
+        }
+        uint32_t r = lo, val = 0;
+        while (e < e_end) {
+          while (r + 1 < nr && e >= starts[r + 1]) ++r;
+          uint32_t run_end = min(starts[r + 1], e_end);
+          if (run_end <= e) break;
+          uint32_t len = run_end - e;
+          if (src[uint64_t(r0 + r) * STR + 4] != 0) {
+            uint32_t m = len >= 32 ? 0xffffffffu : ((1u << len) - 1u);
+            val |= m << uint32_t(dst_bit + e - wb);
+          }
+          e = run_end;
+        }
+        bool partial = (wb < dst_bit) || (wb + 32 > dst_bit + n) || (lo_abs != wb) || (hi_abs != wb + 32);
+        if (partial) {
+          if (val) atomicOr(words + w, val);
+        } else words[w] = val;
+      }
+    }
+    done = hi;
+    __syncthreads();
+  }
+  cx.ar = mark;
+  return true; // the reference loop also ends quietly when the runs are exhausted (rle.rs:43)
+}
+
+// decompress_boolean (boolean/mod.rs:63-102)
+__device__ bool decode_boolean(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, uint8_t *dst_bitmap,
+                               uint64_t dst_bit) {
+  if (avail < 9) {
+    cx.flag(SB_IO);
+    return false;
+  }
+  int codec = src[0];
+  uint32_t compressed = ld_u32u(src + 1);
+  const uint8_t *body = src + 9;
+  uint32_t body_avail = avail - 9;
+  if (compressed > body_avail) {
+    cx.flag(SB_IO);
+    return false;
+  }
+  uint32_t nbytes = (n + 7) >> 3;
+  switch (codec) {
+  case SB_C_NONE: {
+    if (compressed != nbytes) {
+      cx.flag(SB_PANIC);
+      return false;
+    }
+    BitsPacked bs{body};
+    emit_bits(dst_bitmap, dst_bit, n, bs);
+    return true;
+  }
+  case SB_C_LZ4: {
+    Arena mark = cx.ar;
+    uint8_t *tmp = static_cast<uint8_t *>(cx.ar.alloc(uint64_t(nbytes) + 16));
+    if (!tmp) {
+      cx.flag(SB_NYI);
+      return false;
+    }
+    if (!dec_basic(cx, codec, body, compressed, tmp, nbytes)) return false;
+    BitsPacked bs{tmp};
+    emit_bits(dst_bitmap, dst_bit, n, bs);
+    __syncthreads();
+    cx.ar = mark;
+    return true;
+  }
+  case SB_C_RLE: return dec_bool_rle(cx, body, min(compressed, body_avail), n, dst_bitmap, dst_bit);
+  case SB_C_ONEVALUE: {
+    if (body_avail == 0) { // boolean/one_value.rs:55-57
+      cx.flag(SB_OUT_OF_SPEC);
+      return false;
+    }
+    BitsConst bs{body[0] > 0};
+    emit_bits(dst_bitmap, dst_bit, n, bs);
+    return true;
+  }
+  case SB_C_ZSTD:
+  case SB_C_SNAPPY: cx.flag(SB_NYI); return false;
+  default: cx.flag(SB_OUT_OF_SPEC); return false;
+  }
+}
+
+// read_validity (read_basic.rs:36-63): [u32 L][ULEB((ceil8(n)<<1)|1)][bitmap]; L == 0
+// pushes nothing.  Returns the byte offset of the value block, or 0xffffffff on failure.
+__device__ uint32_t decode_validity(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, uint8_t *dst_bitmap,
+                                    uint64_t dst_bit) {
+  if (avail < 4) {
+    cx.flag(SB_IO);
+    return 0xffffffffu;
+  }
+  uint32_t L = ld_u32u(src);
+  if (L > avail - 4) {
+    cx.flag(SB_IO);
+    return 0xffffffffu;
+  }
+  if (L == 0) return 4;
+  // one bit-packed hybrid-RLE run (parquet2 encode_bool); RLE runs are `unreachable!()` upstream
+  const uint8_t *p = src + 4;
+  uint64_t header = 0;
+  uint32_t used = 0;
+  for (uint32_t i = 0; i < L && i < 10; ++i) {
+    uint32_t b = p[i];
+    header |= uint64_t(b & 0x7f) << (7 * i);
+    if (!(b & 0x80)) {
+      used = i + 1;
+      break;
+    }
+  }
+  if (used == 0 || !(header & 1)) {
+    cx.flag(SB_PANIC);
+    return 0xffffffffu;
+  }
+  uint64_t bytes = header >> 1;
+  if (bytes > L - used) bytes = L - used;
+  if (bytes * 8 < n) {
+    cx.flag(SB_PANIC);
+    return 0xffffffffu;
+  }
+  BitsPacked bs{p + used};
+  emit_bits(dst_bitmap, dst_bit, n, bs);
+  return 4 + L;
+}
+
+} // namespace sb

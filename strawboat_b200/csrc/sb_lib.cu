@@ -1,0 +1,565 @@
+// sb_lib.cu -- kernels + C ABI of libstrawboat_b200.so (see include/strawboat_b200.h).
+//
+// Decode pipeline of one sb_decode_columns call:
+//   host : page table (PageDesc per page, WorkItem per CTA job) -> pinned -> H2D
+//   D0/1 : sb_size_kernel   binary columns only: value bytes per page      (two-pass sizing)
+//          sb_scan_kernel   per-column exclusive scan of those sizes
+//   D*   : sb_decode_kernel persistent grid, one CTA (128 thr) per page at a time: TMA bulk
+//          load of the page into shared memory, codec dispatch, coalesced 16-byte stores
+// There is no CPU fallback anywhere: without a CUDA device every entry point returns SB_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sb_common.cuh"
+#include "sb_decode.cuh"
+
+namespace sb {
+
+constexpr uint32_t kSmemMax = 74 * 1024;     // dynamic shared memory per CTA: 3 CTAs / SM
+constexpr uint32_t kSmemMin = 40 * 1024;
+constexpr uint32_t kArenaMin = 6 * 1024;     // arena left after the largest staged page
+constexpr uint32_t kTileBytes = 64 * 1024;   // output bytes per work item of an unstaged page
+constexpr uint32_t kTmaChunk = 32 * 1024;
+
+__device__ __forceinline__ bool is_fixed_type(int t) { return t >= SB_I8 && t <= SB_F64; }
+
+// ------------------------------------------------------------------------------------
+// main decode kernel
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SB_NT)
+    sb_decode_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols,
+                     const WorkItem *__restrict__ items, uint32_t n_items, uint32_t *counter, uint8_t *scratch,
+                     uint64_t scratch_per_cta, int32_t *status, uint32_t stage_cap, uint32_t smem_bytes) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_err;
+  __shared__ uint32_t s_ws[SB_NWARP + 1];
+  __shared__ int s_bcast[4];
+  __shared__ uint32_t s_item;
+
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+
+  for (;;) {
+    if (tid == 0) {
+      s_item = atomicAdd(counter, 1u);
+      s_err = 0;
+    }
+    __syncthreads();
+    const uint32_t it = s_item;
+    if (it >= n_items) break;
+    const WorkItem wi = items[it];
+    const PageDesc pg = pages[wi.page];
+    const ColDesc col = cols[pg.col];
+    const bool staged = pg.len + 32 <= stage_cap;
+
+    Dctx cx;
+    cx.err = &s_err;
+    cx.ws = s_ws;
+    cx.bcast = s_bcast;
+    cx.ar.g_cur = scratch + uint64_t(blockIdx.x) * scratch_per_cta;
+    cx.ar.g_end = cx.ar.g_cur + scratch_per_cta;
+    cx.ar.s_end = dsm + smem_bytes;
+
+    const uint8_t *p;
+    if (staged) {
+      const uint32_t mis = uint32_t(uintptr_t(pg.src) & 15);
+      const uint32_t bytes = (mis + pg.len + 15) & ~15u;
+      if (tid == 0 && bytes) {
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar, bytes);
+        const uint8_t *g = pg.src - mis;
+        for (uint32_t o = 0; o < bytes; o += kTmaChunk) tma_load_1d(dsm + o, g + o, min(kTmaChunk, bytes - o), &s_bar);
+      }
+      if (bytes) {
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+      }
+      p = dsm + mis;
+      cx.ar.s_cur = dsm + ((bytes + 15) & ~15u) + 16; // 16 bytes of slack after the page
+    } else {
+      p = pg.src;
+      cx.ar.s_cur = dsm;
+    }
+
+    const uint32_t avail = pg.len;
+    uint32_t n = pg.num_values;
+    bool ok = true;
+
+    if (col.type == SB_NULL) {
+      // null.rs: length only, nothing to decode
+    } else if (!staged && wi.tile != 0xffffffffu && is_fixed_type(col.type) && !col.nullable) {
+      // ---- oversized page (e.g. max_page_size = None): None / OneValue are split into
+      //      tiles that stream straight from global memory; anything else runs on tile 0.
+      int codec = avail >= 9 ? int(p[0]) : -1;
+      uint32_t compressed = avail >= 9 ? ld_u32u(p + 1) : 0;
+      const uint32_t W = uint32_t(col.W);
+      const uint32_t tile_elems = kTileBytes / W;
+      uint32_t lo = min(n, wi.tile * tile_elems), hi = min(n, lo + tile_elems);
+      uint8_t *dst = col.values + pg.out_elem * W;
+      if (codec == SB_C_NONE && avail >= 9 && compressed <= avail - 9 && uint64_t(compressed) == uint64_t(n) * W) {
+        copy_bytes(dst + uint64_t(lo) * W, p + 9 + uint64_t(lo) * W, uint64_t(hi - lo) * W);
+      } else if (codec == SB_C_ONEVALUE && avail >= 9 + W) {
+        switch (W) {
+        case 1: dec_onevalue<1>(cx, p + 9, avail - 9, lo, hi, dst); break;
+        case 2: dec_onevalue<2>(cx, p + 9, avail - 9, lo, hi, dst); break;
+        case 4: dec_onevalue<4>(cx, p + 9, avail - 9, lo, hi, dst); break;
+        default: dec_onevalue<8>(cx, p + 9, avail - 9, lo, hi, dst); break;
+        }
+      } else if (wi.tile == 0) {
+        uint32_t used = 0;
+        ok = decode_fixed<0>(cx, p, avail, n, col.W, col.is_float != 0, dst, &used);
+      }
+    } else if (wi.tile == 0 || wi.tile == 0xffffffffu) {
+      uint32_t vb = 0;
+      if (col.nullable) {
+        vb = decode_validity(cx, p, avail, n, col.validity, pg.out_elem);
+        if (vb == 0xffffffffu) ok = false;
+      }
+      if (ok) {
+        if (col.type == SB_BOOL) {
+          ok = decode_boolean(cx, p + vb, avail - vb, n, col.values, pg.out_elem);
+        } else if (is_fixed_type(col.type)) {
+          uint32_t used = 0;
+          ok = decode_fixed<0>(cx, p + vb, avail - vb, n, col.W, col.is_float != 0,
+                               col.values + pg.out_elem * uint64_t(col.W), &used);
+        } else {
+          cx.flag(SB_NYI);
+        }
+      }
+    }
+    (void)ok;
+    __syncthreads(); // all reads of the staged page / arena done before the next TMA lands
+    if (tid == 0 && s_err) atomicCAS(status + wi.page, 0, s_err);
+  }
+}
+
+} // namespace sb
+
+// =====================================================================================
+// host side
+// =====================================================================================
+using namespace sb;
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+struct Owner { // allocations handed to the caller through sb_column_out / sb_encoded_column
+  std::vector<void *> dev;
+  std::vector<void *> host_pinned;
+  std::vector<void *> host_malloc;
+};
+
+} // namespace
+
+struct sb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  DevBuf d_tables, d_scratch, d_misc;
+  void *h_tables = nullptr;
+  size_t h_tables_cap = 0;
+  sb_stats stats{};
+};
+
+namespace {
+
+int fail(sb_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+#define SB_CUDA_CHECK(ctx, call)                                                                          \
+  do {                                                                                                    \
+    cudaError_t e__ = (call);                                                                             \
+    if (e__ != cudaSuccess) return fail(ctx, SB_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+int dev_reserve(sb_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return SB_OK;
+  if (b.p) SB_CUDA_CHECK(ctx, cudaFreeAsync(b.p, ctx->stream));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t cap = std::max(bytes, size_t(1) << 20);
+  SB_CUDA_CHECK(ctx, cudaMallocAsync(&b.p, cap, ctx->stream));
+  b.cap = cap;
+  return SB_OK;
+}
+int host_tables_reserve(sb_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->h_tables_cap) return SB_OK;
+  if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
+  ctx->h_tables = nullptr;
+  size_t cap = std::max(bytes, size_t(1) << 20);
+  SB_CUDA_CHECK(ctx, cudaMallocHost(&ctx->h_tables, cap));
+  ctx->h_tables_cap = cap;
+  return SB_OK;
+}
+
+int type_width(int t) {
+  switch (t) {
+  case SB_I8:
+  case SB_U8: return 1;
+  case SB_I16:
+  case SB_U16: return 2;
+  case SB_I32:
+  case SB_U32:
+  case SB_F32: return 4;
+  case SB_I64:
+  case SB_U64:
+  case SB_F64: return 8;
+  case SB_BINARY: return 4;
+  case SB_LARGE_BINARY: return 8;
+  }
+  return 0;
+}
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+} // namespace
+
+extern "C" {
+
+const char *sb_version(void) { return "strawboat_b200 0.1 (sm_100a)"; }
+
+int32_t sb_ctx_create(int32_t device, sb_ctx **out) {
+  if (!out) return SB_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return SB_CUDA; // no CPU fallback
+  sb_ctx *ctx = new (std::nothrow) sb_ctx();
+  if (!ctx) return SB_CUDA;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return SB_CUDA;
+  }
+  ctx->own_stream = true;
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  // keep freed blocks cached in the stream-ordered pool: steady-state calls do not hit the driver
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~uint64_t(0);
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaFuncSetAttribute(sb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemMax));
+  *out = ctx;
+  return SB_OK;
+}
+
+void sb_ctx_destroy(sb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (DevBuf *b : {&ctx->d_tables, &ctx->d_scratch, &ctx->d_misc})
+    if (b->p) cudaFreeAsync(b->p, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int32_t sb_ctx_set_stream(sb_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return SB_INVALID_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  return SB_OK;
+}
+
+const char *sb_last_error(const sb_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context (CUDA device unavailable)"; }
+
+int32_t sb_last_stats(const sb_ctx *ctx, sb_stats *out) {
+  if (!ctx || !out) return SB_INVALID_ARG;
+  *out = ctx->stats;
+  return SB_OK;
+}
+
+void sb_release_columns(sb_ctx *ctx, sb_column_out *outs, uint64_t n) {
+  if (!ctx || !outs) return;
+  cudaSetDevice(ctx->device);
+  for (uint64_t i = 0; i < n; ++i) {
+    Owner *o = static_cast<Owner *>(outs[i]._owner);
+    if (!o) continue;
+    for (void *p : o->dev) cudaFreeAsync(p, ctx->stream);
+    for (void *p : o->host_pinned) cudaFreeHost(p);
+    for (void *p : o->host_malloc) std::free(p);
+    delete o;
+    std::memset(&outs[i], 0, sizeof(outs[i]));
+  }
+}
+
+int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, int32_t out_mem, sb_column_out *outs) {
+  if (!ctx) return SB_CUDA;
+  if (!cols || !outs || (out_mem != SB_MEM_HOST && out_mem != SB_MEM_DEVICE)) return fail(ctx, SB_INVALID_ARG, "bad arguments");
+  SB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  std::memset(outs, 0, sizeof(sb_column_out) * n_cols);
+  ctx->stats = sb_stats{};
+
+  // ---- host pass: sizes, page table
+  uint64_t n_pages_total = 0;
+  for (uint64_t c = 0; c < n_cols; ++c) {
+    const sb_column_in &ci = cols[c];
+    if (ci.leaf.type < SB_NULL || ci.leaf.type > SB_LARGE_BINARY) return fail(ctx, SB_NYI, "unsupported physical type");
+    if (ci.leaf.n_nested > 1) return fail(ctx, SB_NYI, "nested leaves: not implemented yet");
+    if (ci.leaf.type == SB_BINARY || ci.leaf.type == SB_LARGE_BINARY) return fail(ctx, SB_NYI, "binary leaves: not implemented yet");
+    if (ci.n_pages && !ci.metas) return fail(ctx, SB_INVALID_ARG, "metas is NULL");
+    if (ci.nbytes && !ci.bytes) return fail(ctx, SB_INVALID_ARG, "bytes is NULL");
+    n_pages_total += ci.n_pages;
+  }
+  std::vector<Owner *> owners(n_cols, nullptr);
+  auto cleanup = [&]() {
+    for (uint64_t c = 0; c < n_cols; ++c) {
+      outs[c]._owner = owners[c];
+    }
+    sb_release_columns(ctx, outs, n_cols);
+  };
+
+  // table layout in one pinned staging buffer: [ColDesc * n_cols][PageDesc * P][WorkItem * I]
+  uint64_t n_items = 0;
+  uint32_t max_stage = 0;
+  uint64_t max_elems_bytes = 0;
+  const uint32_t stage_cap = kSmemMax - kArenaMin;
+  for (uint64_t c = 0; c < n_cols; ++c) {
+    const sb_column_in &ci = cols[c];
+    const uint64_t W = std::max(1, type_width(ci.leaf.type));
+    for (uint64_t p = 0; p < ci.n_pages; ++p) {
+      const sb_page_meta &m = ci.metas[p];
+      if (m.length > 0xffffffffull || m.num_values > 0xffffffffull) return fail(ctx, SB_OUT_OF_SPEC, "page larger than 4 GiB (u32 size fields)");
+      if (m.length + 32 <= stage_cap) {
+        n_items += 1;
+        max_stage = std::max<uint32_t>(max_stage, uint32_t(m.length));
+      } else {
+        uint64_t out_bytes = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * W;
+        bool tiled = !ci.leaf.nullable && ci.leaf.type >= SB_I8 && ci.leaf.type <= SB_F64;
+        n_items += tiled ? std::max<uint64_t>(1, (out_bytes + kTileBytes - 1) / kTileBytes) : 1;
+      }
+      max_elems_bytes = std::max<uint64_t>(max_elems_bytes, m.num_values * std::max<uint64_t>(W, 4));
+    }
+  }
+  size_t off_cols = 0;
+  size_t off_pages = align_up(off_cols + sizeof(ColDesc) * n_cols, 16);
+  size_t off_items = align_up(off_pages + sizeof(PageDesc) * n_pages_total, 16);
+  size_t tables_bytes = align_up(off_items + sizeof(WorkItem) * n_items, 16);
+  size_t off_status = tables_bytes; // device only (zeroed): status[P] + counter
+  size_t misc_bytes = align_up(sizeof(int32_t) * n_pages_total + 16, 16);
+  int rc;
+  if ((rc = host_tables_reserve(ctx, tables_bytes + misc_bytes))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_tables, tables_bytes + misc_bytes))) return rc;
+  uint8_t *hT = static_cast<uint8_t *>(ctx->h_tables);
+  uint8_t *dT = static_cast<uint8_t *>(ctx->d_tables.p);
+  ColDesc *h_cols = reinterpret_cast<ColDesc *>(hT + off_cols);
+  PageDesc *h_pages = reinterpret_cast<PageDesc *>(hT + off_pages);
+  WorkItem *h_items = reinterpret_cast<WorkItem *>(hT + off_items);
+
+  uint64_t pi = 0, ii = 0, bytes_in = 0, bytes_out = 0;
+  std::vector<void *> d_inputs; // device copies of host inputs, freed at the end of the call
+  for (uint64_t c = 0; c < n_cols; ++c) {
+    const sb_column_in &ci = cols[c];
+    Owner *ow = new Owner();
+    owners[c] = ow;
+    const int W = type_width(ci.leaf.type);
+    uint64_t rows = 0, total_len = 0;
+    for (uint64_t p = 0; p < ci.n_pages; ++p) {
+      rows += ci.metas[p].num_values;
+      total_len += ci.metas[p].length;
+    }
+    if (total_len > ci.nbytes) {
+      cleanup();
+      return fail(ctx, SB_IO, "column bytes shorter than the sum of its page lengths");
+    }
+    // input
+    const uint8_t *d_in = ci.bytes;
+    if (ci.mem == SB_MEM_HOST && total_len) {
+      void *d = nullptr;
+      SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, align_up(total_len + 32, 256), st));
+      d_inputs.push_back(d);
+      SB_CUDA_CHECK(ctx, cudaMemcpyAsync(d, ci.bytes, total_len, cudaMemcpyHostToDevice, st));
+      d_in = static_cast<const uint8_t *>(d);
+    }
+    // outputs
+    sb_column_out &o = outs[c];
+    o.length = rows;
+    o.mem = out_mem;
+    ColDesc &cd = h_cols[c];
+    std::memset(&cd, 0, sizeof(cd));
+    cd.type = ci.leaf.type;
+    cd.nullable = ci.leaf.nullable != 0 && ci.leaf.type != SB_NULL;
+    cd.W = W;
+    cd.is_float = ci.leaf.type == SB_F32 || ci.leaf.type == SB_F64;
+    cd.length = rows;
+    uint64_t bitmap_bytes = align_up((rows + 7) / 8, 4);
+    if (ci.leaf.type == SB_BOOL) {
+      o.values_bytes = (rows + 7) / 8;
+      void *d = nullptr;
+      SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, bitmap_bytes + 16, st));
+      ow->dev.push_back(d);
+      SB_CUDA_CHECK(ctx, cudaMemsetAsync(d, 0, bitmap_bytes + 16, st));
+      cd.values = static_cast<uint8_t *>(d);
+    } else if (W && ci.leaf.type != SB_NULL) {
+      o.values_bytes = rows * uint64_t(W);
+      void *d = nullptr;
+      SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, o.values_bytes + 16, st));
+      ow->dev.push_back(d);
+      cd.values = static_cast<uint8_t *>(d);
+    }
+    if (cd.nullable) {
+      o.validity_bytes = (rows + 7) / 8;
+      void *d = nullptr;
+      SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, bitmap_bytes + 16, st));
+      ow->dev.push_back(d);
+      SB_CUDA_CHECK(ctx, cudaMemsetAsync(d, 0, bitmap_bytes + 16, st));
+      cd.validity = static_cast<uint8_t *>(d);
+    }
+    bytes_out += o.values_bytes + o.validity_bytes;
+    // pages
+    uint64_t src_off = 0, elem = 0;
+    for (uint64_t p = 0; p < ci.n_pages; ++p) {
+      const sb_page_meta &m = ci.metas[p];
+      PageDesc &pd = h_pages[pi];
+      pd.src = d_in + src_off;
+      pd.len = uint32_t(m.length);
+      pd.num_values = uint32_t(m.num_values);
+      pd.col = uint32_t(c);
+      pd.ordinal = uint32_t(p);
+      pd.out_elem = elem;
+      pd.out_byte = 0;
+      if (m.length + 32 <= stage_cap) {
+        h_items[ii++] = WorkItem{uint32_t(pi), 0xffffffffu};
+      } else {
+        uint64_t out_b = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * uint64_t(std::max(1, W));
+        bool tiled = !ci.leaf.nullable && ci.leaf.type >= SB_I8 && ci.leaf.type <= SB_F64;
+        uint64_t nt = tiled ? std::max<uint64_t>(1, (out_b + kTileBytes - 1) / kTileBytes) : 1;
+        for (uint64_t t = 0; t < nt; ++t) h_items[ii++] = WorkItem{uint32_t(pi), uint32_t(t)};
+      }
+      src_off += m.length;
+      elem += m.num_values;
+      bytes_in += m.length;
+      ++pi;
+    }
+  }
+
+  // ---- launch configuration
+  uint32_t smem = uint32_t(align_up(std::min<uint64_t>(uint64_t(max_stage) + 48, stage_cap) + kArenaMin, 1024));
+  smem = std::min(std::max(smem, kSmemMin), kSmemMax);
+  int occ = 1;
+  SB_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_decode_kernel, SB_NT, smem));
+  occ = std::max(1, occ);
+  uint32_t grid = uint32_t(std::min<uint64_t>(n_items, uint64_t(ctx->sm_count) * occ));
+  uint64_t scratch_per_cta = align_up(3 * (max_elems_bytes + 64) + 16 * 1024, 256);
+  if (n_items) {
+    if ((rc = dev_reserve(ctx, ctx->d_scratch, scratch_per_cta * grid))) {
+      cleanup();
+      return rc;
+    }
+    SB_CUDA_CHECK(ctx, cudaMemcpyAsync(dT, hT, tables_bytes, cudaMemcpyHostToDevice, st));
+    SB_CUDA_CHECK(ctx, cudaMemsetAsync(dT + off_status, 0, misc_bytes, st));
+    int32_t *d_status = reinterpret_cast<int32_t *>(dT + off_status);
+    uint32_t *d_counter = reinterpret_cast<uint32_t *>(dT + off_status + sizeof(int32_t) * n_pages_total);
+    SB_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, st));
+    sb_decode_kernel<<<grid, SB_NT, smem, st>>>(reinterpret_cast<const PageDesc *>(dT + off_pages),
+                                                reinterpret_cast<const ColDesc *>(dT + off_cols),
+                                                reinterpret_cast<const WorkItem *>(dT + off_items), uint32_t(n_items),
+                                                d_counter, static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta,
+                                                d_status, stage_cap, smem);
+    SB_CUDA_CHECK(ctx, cudaGetLastError());
+    SB_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->stats.kernel_launches = 1;
+    // statuses back (pinned), reuse the tail of the host table buffer
+    SB_CUDA_CHECK(ctx, cudaMemcpyAsync(hT + off_status, dT + off_status, sizeof(int32_t) * n_pages_total, cudaMemcpyDeviceToHost, st));
+  }
+
+  // ---- results to the caller
+  for (uint64_t c = 0; c < n_cols; ++c) {
+    sb_column_out &o = outs[c];
+    Owner *ow = owners[c];
+    const ColDesc &cd = h_cols[c];
+    if (out_mem == SB_MEM_DEVICE) {
+      o.values = cd.values;
+      o.validity = cd.validity;
+    } else {
+      if (cd.values && o.values_bytes) {
+        void *h = nullptr;
+        SB_CUDA_CHECK(ctx, cudaMallocHost(&h, o.values_bytes));
+        ow->host_pinned.push_back(h);
+        SB_CUDA_CHECK(ctx, cudaMemcpyAsync(h, cd.values, o.values_bytes, cudaMemcpyDeviceToHost, st));
+        o.values = h;
+      }
+      if (cd.validity && o.validity_bytes) {
+        void *h = nullptr;
+        SB_CUDA_CHECK(ctx, cudaMallocHost(&h, o.validity_bytes));
+        ow->host_pinned.push_back(h);
+        SB_CUDA_CHECK(ctx, cudaMemcpyAsync(h, cd.validity, o.validity_bytes, cudaMemcpyDeviceToHost, st));
+        o.validity = static_cast<uint8_t *>(h);
+      }
+    }
+  }
+  for (void *d : d_inputs) cudaFreeAsync(d, st);
+  SB_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  if (out_mem == SB_MEM_HOST) { // device copies no longer needed
+    for (uint64_t c = 0; c < n_cols; ++c) {
+      for (void *p : owners[c]->dev) cudaFreeAsync(p, st);
+      owners[c]->dev.clear();
+    }
+  }
+  if (n_items) cudaEventElapsedTime(&ctx->stats.device_ms, ctx->ev0, ctx->ev1);
+
+  int32_t first_err = SB_OK;
+  const int32_t *h_status = reinterpret_cast<const int32_t *>(hT + off_status);
+  pi = 0;
+  for (uint64_t c = 0; c < n_cols; ++c) {
+    sb_column_out &o = outs[c];
+    o._owner = owners[c];
+    int32_t *ps = static_cast<int32_t *>(std::malloc(sizeof(int32_t) * std::max<uint64_t>(1, cols[c].n_pages)));
+    owners[c]->host_malloc.push_back(ps);
+    o.page_status = ps;
+    for (uint64_t p = 0; p < cols[c].n_pages; ++p, ++pi) {
+      ps[p] = h_status[pi];
+      if (ps[p] != SB_OK && first_err == SB_OK) {
+        first_err = ps[p];
+        ctx->err = "page " + std::to_string(p) + " of column " + std::to_string(c) + " failed with status " + std::to_string(ps[p]);
+      }
+    }
+  }
+  ctx->stats.pages = n_pages_total;
+  ctx->stats.bytes_in = bytes_in;
+  ctx->stats.bytes_out = bytes_out;
+  return first_err;
+}
+
+int32_t sb_decode_pages(sb_ctx *ctx, const sb_column_in *pages, uint64_t n_pages, int32_t out_mem, sb_column_out *outs) {
+  if (!ctx) return SB_CUDA;
+  for (uint64_t i = 0; i < n_pages; ++i)
+    if (pages[i].n_pages != 1) return fail(ctx, SB_INVALID_ARG, "sb_decode_pages: every entry must hold exactly one page");
+  return sb_decode_columns(ctx, pages, n_pages, out_mem, outs);
+}
+
+int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *, uint64_t, const sb_write_options *, int32_t, sb_encoded_column *) {
+  if (!ctx) return SB_CUDA;
+  return fail(ctx, SB_NYI, "sb_encode_columns: not implemented yet");
+}
+void sb_release_encoded(sb_ctx *, sb_encoded_column *, uint64_t) {}
+
+} // extern "C"
