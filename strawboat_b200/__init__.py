@@ -61,6 +61,7 @@ class Column:
         self.type = type_
         self.metas = list(metas)
         self._keep = None
+        self._metas_c = None
         if hasattr(data, "data_ptr"):  # torch tensor
             assert data.is_cuda and data.is_contiguous() and data.element_size() == 1
             self.ptr, self.nbytes, self.mem = data.data_ptr(), data.numel(), MEM_DEVICE
@@ -69,6 +70,15 @@ class Column:
             arr = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, dtype=np.uint8)
             self._keep = arr
             self.ptr, self.nbytes, self.mem = (arr.ctypes.data if arr.size else 0), arr.size, MEM_HOST
+
+
+    def metas_c(self):
+        """PageMeta[] for the C ABI (built once per Column)."""
+        if self._metas_c is None:
+            a = np.array(self.metas, dtype=np.uint64).reshape(-1, 2) if self.metas else np.zeros((1, 2), np.uint64)
+            self._metas_np = np.ascontiguousarray(a)
+            self._metas_c = C.cast(self._metas_np.ctypes.data, C.POINTER(_capi.PageMeta))
+        return self._metas_c
 
 
 class _DevArray:
@@ -176,9 +186,7 @@ class Context:
             ins[i].bytes = col.ptr
             ins[i].nbytes = col.nbytes
             ins[i].mem = col.mem
-            m = (_capi.PageMeta * max(1, len(col.metas)))()
-            for j, (length, nv) in enumerate(col.metas):
-                m[j].length, m[j].num_values = length, nv
+            m = col.metas_c()
             keep.append(m)
             ins[i].metas = m
             ins[i].n_pages = len(col.metas)

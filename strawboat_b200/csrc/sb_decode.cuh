@@ -11,6 +11,7 @@
 // output it reproduces bit for bit.
 #pragma once
 #include "sb_common.cuh"
+#include "sb_lz4.cuh"
 
 namespace sb {
 
@@ -80,78 +81,6 @@ __device__ __forceinline__ void copy_bytes(uint8_t *dst, const uint8_t *src, uin
   for (uint64_t i = (nvec << 4) + tid; i < nbytes; i += SB_NT) dst[i] = src[i];
 }
 
-// ------------------------------------------------------------------------------------
-// LZ4 block decode by ONE warp (basic.rs:87-91 -> LZ4_decompress_safe with a known output
-// size).  Token stream is serial; literal and match copies are lane-parallel.  Overlapping
-// matches (offset < length) are resolved as dst[op+i] = dst[op-offset + i % offset], whose
-// sources all precede `op`, so the whole match is one parallel step.
-// Returns 0 or SB_EXTERNAL (uniform across the warp).
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ int lz4_decode_warp(const uint8_t *src, uint32_t clen, uint8_t *dst, uint32_t dlen) {
-  const uint32_t lane = threadIdx.x & 31;
-  uint32_t ip = 0, op = 0;
-  if (clen == 0) return dlen == 0 ? 0 : SB_EXTERNAL;
-  for (;;) {
-    if (ip >= clen) return SB_EXTERNAL;
-    uint32_t token = src[ip++];
-    uint32_t lit = token >> 4;
-    if (lit == 15) {
-      uint32_t b;
-      do {
-        if (ip >= clen) return SB_EXTERNAL;
-        b = src[ip++];
-        lit += b;
-      } while (b == 255);
-    }
-    if (lit > clen - ip || lit > dlen - op) return SB_EXTERNAL;
-    if (lit) {
-      const uint8_t *s = src + ip;
-      uint8_t *d = dst + op;
-      if (lit >= 256) { // long literal run: vectorise the aligned body
-        uint32_t head = min(lit, uint32_t((16 - (uintptr_t(d) & 15)) & 15));
-        for (uint32_t i = lane; i < head; i += 32) d[i] = s[i];
-        uint32_t nvec = (lit - head) >> 4;
-        for (uint32_t v = lane; v < nvec; v += 32)
-          *reinterpret_cast<uint4 *>(d + head + (v << 4)) = ld_u128u(s + head + (v << 4));
-        for (uint32_t i = head + (nvec << 4) + lane; i < lit; i += 32) d[i] = s[i];
-      } else {
-        for (uint32_t i = lane; i < lit; i += 32) d[i] = s[i];
-      }
-    }
-    ip += lit;
-    op += lit;
-    if (ip == clen) break; // last sequence carries literals only
-    if (clen - ip < 2) return SB_EXTERNAL;
-    uint32_t offset = uint32_t(src[ip]) | (uint32_t(src[ip + 1]) << 8);
-    ip += 2;
-    if (offset == 0 || offset > op) return SB_EXTERNAL;
-    uint32_t ml = token & 15;
-    if (ml == 15) {
-      uint32_t b;
-      do {
-        if (ip >= clen) return SB_EXTERNAL;
-        b = src[ip++];
-        ml += b;
-      } while (b == 255);
-    }
-    ml += 4;
-    if (ml > dlen - op) return SB_EXTERNAL;
-    __syncwarp();
-    {
-      uint8_t *d = dst + op;
-      const uint8_t *m = d - offset;
-      if (offset >= ml) {
-        for (uint32_t i = lane; i < ml; i += 32) d[i] = m[i];
-      } else {
-        for (uint32_t i = lane; i < ml; i += 32) d[i] = m[i % offset];
-      }
-    }
-    op += ml;
-    __syncwarp();
-  }
-  return op == dlen ? 0 : SB_EXTERNAL;
-}
-
 // Basic codecs (CommonCompression::decompress, basic.rs:62-72) into `dst`.
 __device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *src, uint32_t clen, uint8_t *dst,
                                           uint64_t out_bytes) {
@@ -166,7 +95,8 @@ __device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *sr
   if (codec == SB_C_LZ4) {
     __syncthreads();
     if (threadIdx.x < 32) {
-      int rc = lz4_decode_warp(src, clen, dst, uint32_t(out_bytes));
+      FlatOut fo{dst};
+      int rc = lz4_decode_warp2(src, clen, fo, uint32_t(out_bytes));
       if (threadIdx.x == 0) cx.bcast[0] = rc;
     }
     __syncthreads();

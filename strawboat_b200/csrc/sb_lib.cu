@@ -20,13 +20,87 @@
 
 namespace sb {
 
+__device__ __forceinline__ bool is_fixed_type(int t) { return t >= SB_I8 && t <= SB_F64; }
+
 constexpr uint32_t kSmemMax = 74 * 1024;     // dynamic shared memory per CTA: 3 CTAs / SM
 constexpr uint32_t kSmemMin = 40 * 1024;
 constexpr uint32_t kArenaMin = 6 * 1024;     // arena left after the largest staged page
 constexpr uint32_t kTileBytes = 64 * 1024;   // output bytes per work item of an unstaged page
 constexpr uint32_t kTmaChunk = 32 * 1024;
 
-__device__ __forceinline__ bool is_fixed_type(int t) { return t >= SB_I8 && t <= SB_F64; }
+
+
+// ------------------------------------------------------------------------------------
+// LZ4 side path.  Top-level LZ4 value blocks of fixed-width columns are inherently serial
+// per page, so they run in their own kernel (one WARP per page, shared-memory ring, many
+// pages in flight per SM) concurrently with the main kernel instead of pinning a whole CTA.
+// sb_classify_kernel finds those pages; both kernels apply the same predicate.
+// ------------------------------------------------------------------------------------
+struct Lz4Job {
+  const uint8_t *src;
+  uint8_t *dst;
+  uint32_t clen, dlen, page, pad;
+};
+
+// Parses [validity section][hdr9] of a flat fixed-width page straight from global memory.
+// Returns true when the value block is a top-level LZ4 block with an in-bounds payload.
+__device__ __forceinline__ bool lz4_side_page(const uint8_t *p, uint32_t len, bool nullable, uint32_t *vb_out,
+                                              uint32_t *clen_out) {
+  uint32_t vb = 0;
+  if (nullable) {
+    if (len < 4) return false;
+    uint32_t L = uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
+    if (L > len - 4) return false;
+    vb = 4 + L;
+  }
+  if (len - vb < 9 || p[vb] != SB_C_LZ4) return false;
+  const uint8_t *h = p + vb;
+  uint32_t clen = uint32_t(h[1]) | (uint32_t(h[2]) << 8) | (uint32_t(h[3]) << 16) | (uint32_t(h[4]) << 24);
+  if (clen > len - vb - 9) return false;
+  *vb_out = vb;
+  *clen_out = clen;
+  return true;
+}
+
+__global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, uint32_t n_pages,
+                                   Lz4Job *jobs, uint32_t *n_jobs, uint8_t *side_flags) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pages) return;
+  const PageDesc pg = pages[i];
+  const ColDesc col = cols[pg.col];
+  if (!is_fixed_type(col.type)) return;
+  uint32_t vb, clen;
+  if (!lz4_side_page(pg.src, pg.len, col.nullable != 0, &vb, &clen)) return;
+  uint32_t slot = atomicAdd(n_jobs, 1u);
+  Lz4Job j;
+  j.src = pg.src + vb + 9;
+  j.dst = col.values + pg.out_elem * uint64_t(col.W);
+  j.clen = clen;
+  j.dlen = pg.num_values * uint32_t(col.W);
+  j.page = i;
+  j.pad = 0;
+  jobs[slot] = j;
+  side_flags[i] = 1;
+}
+
+constexpr int kLz4Warps = 2;
+__global__ void __launch_bounds__(kLz4Warps * 32)
+    sb_lz4_kernel(const Lz4Job *__restrict__ jobs, const uint32_t *__restrict__ n_jobs_p, uint32_t *counter, int32_t *status) {
+  __shared__ __align__(16) uint8_t rings[kLz4Warps][SB_LZ4_RING];
+  __shared__ __align__(16) uint8_t in_rings[kLz4Warps][SB_LZ4_IN];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_jobs = *n_jobs_p;
+  for (;;) {
+    uint32_t j = 0;
+    if (lane == 0) j = atomicAdd(counter, 1u);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= n_jobs) break;
+    const Lz4Job job = jobs[j];
+    int rc = lz4_decode_stream(job.src, job.clen, job.dst, job.dlen, in_rings[warp], rings[warp]);
+    if (rc && lane == 0) atomicCAS(status + job.page, 0, rc);
+    __syncwarp();
+  }
+}
 
 // ------------------------------------------------------------------------------------
 // main decode kernel
@@ -34,7 +108,7 @@ __device__ __forceinline__ bool is_fixed_type(int t) { return t >= SB_I8 && t <=
 __global__ void __launch_bounds__(SB_NT)
     sb_decode_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols,
                      const WorkItem *__restrict__ items, uint32_t n_items, uint32_t *counter, uint8_t *scratch,
-                     uint64_t scratch_per_cta, int32_t *status, uint32_t stage_cap, uint32_t smem_bytes) {
+                     uint64_t scratch_per_cta, int32_t *status, uint32_t stage_cap, uint32_t smem_bytes, const uint8_t *__restrict__ side_flags) {
   extern __shared__ __align__(128) uint8_t dsm[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_err;
@@ -61,6 +135,11 @@ __global__ void __launch_bounds__(SB_NT)
     const WorkItem wi = items[it];
     const PageDesc pg = pages[wi.page];
     const ColDesc col = cols[pg.col];
+    const bool lz4_side = side_flags != nullptr && side_flags[wi.page] != 0;
+    if (lz4_side && !col.nullable) { // value block handled by sb_lz4_kernel, nothing else in the page
+      __syncthreads();
+      continue;
+    }
     const bool staged = pg.len + 32 <= stage_cap;
 
     Dctx cx;
@@ -118,7 +197,7 @@ __global__ void __launch_bounds__(SB_NT)
         }
       } else if (wi.tile == 0) {
         uint32_t used = 0;
-        ok = decode_fixed<0>(cx, p, avail, n, col.W, col.is_float != 0, dst, &used);
+        if (!lz4_side) ok = decode_fixed<0>(cx, p, avail, n, col.W, col.is_float != 0, dst, &used);
       }
     } else if (wi.tile == 0 || wi.tile == 0xffffffffu) {
       uint32_t vb = 0;
@@ -131,8 +210,10 @@ __global__ void __launch_bounds__(SB_NT)
           ok = decode_boolean(cx, p + vb, avail - vb, n, col.values, pg.out_elem);
         } else if (is_fixed_type(col.type)) {
           uint32_t used = 0;
-          ok = decode_fixed<0>(cx, p + vb, avail - vb, n, col.W, col.is_float != 0,
-                               col.values + pg.out_elem * uint64_t(col.W), &used);
+          // top-level LZ4 blocks are decoded by sb_lz4_kernel (same predicate as sb_classify_kernel)
+          if (!lz4_side)
+            ok = decode_fixed<0>(cx, p + vb, avail - vb, n, col.W, col.is_float != 0,
+                                 col.values + pg.out_elem * uint64_t(col.W), &used);
         } else {
           cx.flag(SB_NYI);
         }
@@ -157,9 +238,13 @@ struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
 };
+struct PinnedBlock {
+  void *p;
+  size_t cap;
+};
 struct Owner { // allocations handed to the caller through sb_column_out / sb_encoded_column
   std::vector<void *> dev;
-  std::vector<void *> host_pinned;
+  std::vector<PinnedBlock> host_pinned;
   std::vector<void *> host_malloc;
 };
 
@@ -167,15 +252,16 @@ struct Owner { // allocations handed to the caller through sb_column_out / sb_en
 
 struct sb_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, aux = nullptr;
   bool own_stream = false;
   std::string err;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
   int sm_count = 0;
   int max_smem_optin = 0;
-  DevBuf d_tables, d_scratch, d_misc;
+  DevBuf d_tables, d_scratch;
   void *h_tables = nullptr;
   size_t h_tables_cap = 0;
+  std::vector<PinnedBlock> pinned_free; // pinned host blocks are expensive to create: recycled
   sb_stats stats{};
 };
 
@@ -196,7 +282,7 @@ int dev_reserve(sb_ctx *ctx, DevBuf &b, size_t bytes) {
   if (b.p) SB_CUDA_CHECK(ctx, cudaFreeAsync(b.p, ctx->stream));
   b.p = nullptr;
   b.cap = 0;
-  size_t cap = std::max(bytes, size_t(1) << 20);
+  size_t cap = std::max(bytes + bytes / 4, size_t(1) << 20);
   SB_CUDA_CHECK(ctx, cudaMallocAsync(&b.p, cap, ctx->stream));
   b.cap = cap;
   return SB_OK;
@@ -205,10 +291,35 @@ int host_tables_reserve(sb_ctx *ctx, size_t bytes) {
   if (bytes <= ctx->h_tables_cap) return SB_OK;
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
   ctx->h_tables = nullptr;
-  size_t cap = std::max(bytes, size_t(1) << 20);
+  size_t cap = std::max(bytes + bytes / 4, size_t(1) << 20);
   SB_CUDA_CHECK(ctx, cudaMallocHost(&ctx->h_tables, cap));
   ctx->h_tables_cap = cap;
   return SB_OK;
+}
+// best-fit from the recycle list, else a new pinned allocation
+int pinned_get(sb_ctx *ctx, size_t bytes, PinnedBlock *out) {
+  bytes = std::max<size_t>(bytes, 64);
+  int best = -1;
+  for (size_t i = 0; i < ctx->pinned_free.size(); ++i)
+    if (ctx->pinned_free[i].cap >= bytes && ctx->pinned_free[i].cap <= 2 * bytes + 4096 &&
+        (best < 0 || ctx->pinned_free[i].cap < ctx->pinned_free[size_t(best)].cap))
+      best = int(i);
+  if (best >= 0) {
+    *out = ctx->pinned_free[size_t(best)];
+    ctx->pinned_free.erase(ctx->pinned_free.begin() + best);
+    return SB_OK;
+  }
+  void *h = nullptr;
+  SB_CUDA_CHECK(ctx, cudaMallocHost(&h, bytes));
+  *out = PinnedBlock{h, bytes};
+  return SB_OK;
+}
+void pinned_put(sb_ctx *ctx, PinnedBlock b) {
+  if (ctx->pinned_free.size() >= 64) {
+    cudaFreeHost(b.p);
+    return;
+  }
+  ctx->pinned_free.push_back(b);
 }
 
 int type_width(int t) {
@@ -229,6 +340,7 @@ int type_width(int t) {
   return 0;
 }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline bool fixed_type(int t) { return t >= SB_I8 && t <= SB_F64; }
 
 } // namespace
 
@@ -245,13 +357,16 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out) {
   sb_ctx *ctx = new (std::nothrow) sb_ctx();
   if (!ctx) return SB_CUDA;
   ctx->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return SB_CUDA;
   }
   ctx->own_stream = true;
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   // keep freed blocks cached in the stream-ordered pool: steady-state calls do not hit the driver
@@ -269,13 +384,16 @@ void sb_ctx_destroy(sb_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (DevBuf *b : {&ctx->d_tables, &ctx->d_scratch, &ctx->d_misc})
+  cudaStreamSynchronize(ctx->aux);
+  for (DevBuf *b : {&ctx->d_tables, &ctx->d_scratch})
     if (b->p) cudaFreeAsync(b->p, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
+  for (cudaEvent_t ev : {ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->ev_join})
+    if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->aux);
   delete ctx;
 }
 
@@ -303,7 +421,7 @@ void sb_release_columns(sb_ctx *ctx, sb_column_out *outs, uint64_t n) {
     Owner *o = static_cast<Owner *>(outs[i]._owner);
     if (!o) continue;
     for (void *p : o->dev) cudaFreeAsync(p, ctx->stream);
-    for (void *p : o->host_pinned) cudaFreeHost(p);
+    for (auto &b : o->host_pinned) pinned_put(ctx, b);
     for (void *p : o->host_malloc) std::free(p);
     delete o;
     std::memset(&outs[i], 0, sizeof(outs[i]));
@@ -318,8 +436,10 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   std::memset(outs, 0, sizeof(sb_column_out) * n_cols);
   ctx->stats = sb_stats{};
 
-  // ---- host pass: sizes, page table
-  uint64_t n_pages_total = 0;
+  // ---- host pass: validate, count pages / work items
+  uint64_t n_pages_total = 0, n_items = 0, max_elems_bytes = 0;
+  uint32_t max_stage = 0;
+  const uint32_t stage_cap = kSmemMax - kArenaMin;
   for (uint64_t c = 0; c < n_cols; ++c) {
     const sb_column_in &ci = cols[c];
     if (ci.leaf.type < SB_NULL || ci.leaf.type > SB_LARGE_BINARY) return fail(ctx, SB_NYI, "unsupported physical type");
@@ -328,22 +448,6 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     if (ci.n_pages && !ci.metas) return fail(ctx, SB_INVALID_ARG, "metas is NULL");
     if (ci.nbytes && !ci.bytes) return fail(ctx, SB_INVALID_ARG, "bytes is NULL");
     n_pages_total += ci.n_pages;
-  }
-  std::vector<Owner *> owners(n_cols, nullptr);
-  auto cleanup = [&]() {
-    for (uint64_t c = 0; c < n_cols; ++c) {
-      outs[c]._owner = owners[c];
-    }
-    sb_release_columns(ctx, outs, n_cols);
-  };
-
-  // table layout in one pinned staging buffer: [ColDesc * n_cols][PageDesc * P][WorkItem * I]
-  uint64_t n_items = 0;
-  uint32_t max_stage = 0;
-  uint64_t max_elems_bytes = 0;
-  const uint32_t stage_cap = kSmemMax - kArenaMin;
-  for (uint64_t c = 0; c < n_cols; ++c) {
-    const sb_column_in &ci = cols[c];
     const uint64_t W = std::max(1, type_width(ci.leaf.type));
     for (uint64_t p = 0; p < ci.n_pages; ++p) {
       const sb_page_meta &m = ci.metas[p];
@@ -353,21 +457,34 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
         max_stage = std::max<uint32_t>(max_stage, uint32_t(m.length));
       } else {
         uint64_t out_bytes = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * W;
-        bool tiled = !ci.leaf.nullable && ci.leaf.type >= SB_I8 && ci.leaf.type <= SB_F64;
+        bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type);
         n_items += tiled ? std::max<uint64_t>(1, (out_bytes + kTileBytes - 1) / kTileBytes) : 1;
       }
       max_elems_bytes = std::max<uint64_t>(max_elems_bytes, m.num_values * std::max<uint64_t>(W, 4));
     }
   }
+  std::vector<Owner *> owners(n_cols, nullptr);
+  auto cleanup = [&]() {
+    for (uint64_t c = 0; c < n_cols; ++c) outs[c]._owner = owners[c];
+    sb_release_columns(ctx, outs, n_cols);
+  };
+
+  // one pinned staging buffer, mirrored on the device:
+  //   uploaded : [ColDesc * n_cols][PageDesc * P][WorkItem * I]
+  //   zeroed   : [status * P][counters * 4][side_flags * P]      device only: [Lz4Job * P]
   size_t off_cols = 0;
   size_t off_pages = align_up(off_cols + sizeof(ColDesc) * n_cols, 16);
   size_t off_items = align_up(off_pages + sizeof(PageDesc) * n_pages_total, 16);
   size_t tables_bytes = align_up(off_items + sizeof(WorkItem) * n_items, 16);
-  size_t off_status = tables_bytes; // device only (zeroed): status[P] + counter
-  size_t misc_bytes = align_up(sizeof(int32_t) * n_pages_total + 16, 16);
+  size_t off_status = tables_bytes;
+  size_t off_counters = align_up(off_status + sizeof(int32_t) * n_pages_total, 16);
+  size_t off_flags = off_counters + 16;
+  size_t zero_end = align_up(off_flags + n_pages_total, 16);
+  size_t off_jobs = zero_end;
+  size_t dev_bytes = off_jobs + sizeof(Lz4Job) * n_pages_total;
   int rc;
-  if ((rc = host_tables_reserve(ctx, tables_bytes + misc_bytes))) return rc;
-  if ((rc = dev_reserve(ctx, ctx->d_tables, tables_bytes + misc_bytes))) return rc;
+  if ((rc = host_tables_reserve(ctx, zero_end))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_tables, dev_bytes))) return rc;
   uint8_t *hT = static_cast<uint8_t *>(ctx->h_tables);
   uint8_t *dT = static_cast<uint8_t *>(ctx->d_tables.p);
   ColDesc *h_cols = reinterpret_cast<ColDesc *>(hT + off_cols);
@@ -376,11 +493,13 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
 
   uint64_t pi = 0, ii = 0, bytes_in = 0, bytes_out = 0;
   std::vector<void *> d_inputs; // device copies of host inputs, freed at the end of the call
+  bool any_fixed = false;
   for (uint64_t c = 0; c < n_cols; ++c) {
     const sb_column_in &ci = cols[c];
     Owner *ow = new Owner();
     owners[c] = ow;
     const int W = type_width(ci.leaf.type);
+    any_fixed |= fixed_type(ci.leaf.type);
     uint64_t rows = 0, total_len = 0;
     for (uint64_t p = 0; p < ci.n_pages; ++p) {
       rows += ci.metas[p].num_values;
@@ -450,7 +569,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
         h_items[ii++] = WorkItem{uint32_t(pi), 0xffffffffu};
       } else {
         uint64_t out_b = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * uint64_t(std::max(1, W));
-        bool tiled = !ci.leaf.nullable && ci.leaf.type >= SB_I8 && ci.leaf.type <= SB_F64;
+        bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type);
         uint64_t nt = tiled ? std::max<uint64_t>(1, (out_b + kTileBytes - 1) / kTileBytes) : 1;
         for (uint64_t t = 0; t < nt; ++t) h_items[ii++] = WorkItem{uint32_t(pi), uint32_t(t)};
       }
@@ -461,7 +580,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     }
   }
 
-  // ---- launch configuration
+  // ---- launch
   uint32_t smem = uint32_t(align_up(std::min<uint64_t>(uint64_t(max_stage) + 48, stage_cap) + kArenaMin, 1024));
   smem = std::min(std::max(smem, kSmemMin), kSmemMax);
   int occ = 1;
@@ -475,18 +594,35 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       return rc;
     }
     SB_CUDA_CHECK(ctx, cudaMemcpyAsync(dT, hT, tables_bytes, cudaMemcpyHostToDevice, st));
-    SB_CUDA_CHECK(ctx, cudaMemsetAsync(dT + off_status, 0, misc_bytes, st));
+    SB_CUDA_CHECK(ctx, cudaMemsetAsync(dT + off_status, 0, zero_end - off_status, st));
+    const PageDesc *d_pages = reinterpret_cast<const PageDesc *>(dT + off_pages);
+    const ColDesc *d_cols = reinterpret_cast<const ColDesc *>(dT + off_cols);
     int32_t *d_status = reinterpret_cast<int32_t *>(dT + off_status);
-    uint32_t *d_counter = reinterpret_cast<uint32_t *>(dT + off_status + sizeof(int32_t) * n_pages_total);
+    uint32_t *d_counters = reinterpret_cast<uint32_t *>(dT + off_counters); // [0] main queue, [1] lz4 queue, [2] n lz4 jobs
+    uint8_t *d_flags = dT + off_flags;
+    Lz4Job *d_jobs = reinterpret_cast<Lz4Job *>(dT + off_jobs);
     SB_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, st));
-    sb_decode_kernel<<<grid, SB_NT, smem, st>>>(reinterpret_cast<const PageDesc *>(dT + off_pages),
-                                                reinterpret_cast<const ColDesc *>(dT + off_cols),
-                                                reinterpret_cast<const WorkItem *>(dT + off_items), uint32_t(n_items),
-                                                d_counter, static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta,
-                                                d_status, stage_cap, smem);
+    if (any_fixed) {
+      // D0: find top-level LZ4 blocks; run them warp-per-page next to the main kernel
+      sb_classify_kernel<<<uint32_t((n_pages_total + 255) / 256), 256, 0, st>>>(d_pages, d_cols, uint32_t(n_pages_total), d_jobs,
+                                                                              d_counters + 2, d_flags);
+      SB_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_fork, st));
+      SB_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+      int lz4_occ = 1;
+      SB_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz4_occ, sb_lz4_kernel, kLz4Warps * 32, 0));
+      uint32_t lz4_grid = uint32_t(std::min<uint64_t>((n_pages_total + kLz4Warps - 1) / kLz4Warps,
+                                                      uint64_t(ctx->sm_count) * std::max(1, lz4_occ)));
+      sb_lz4_kernel<<<lz4_grid, kLz4Warps * 32, 0, ctx->aux>>>(d_jobs, d_counters + 2, d_counters + 1, d_status);
+      SB_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_join, ctx->aux));
+      ctx->stats.kernel_launches += 2;
+    }
+    sb_decode_kernel<<<grid, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items),
+                                                uint32_t(n_items), d_counters, static_cast<uint8_t *>(ctx->d_scratch.p),
+                                                scratch_per_cta, d_status, stage_cap, smem, any_fixed ? d_flags : nullptr);
     SB_CUDA_CHECK(ctx, cudaGetLastError());
+    if (any_fixed) SB_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     SB_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, st));
-    ctx->stats.kernel_launches = 1;
+    ctx->stats.kernel_launches += 1;
     // statuses back (pinned), reuse the tail of the host table buffer
     SB_CUDA_CHECK(ctx, cudaMemcpyAsync(hT + off_status, dT + off_status, sizeof(int32_t) * n_pages_total, cudaMemcpyDeviceToHost, st));
   }
@@ -501,18 +637,18 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       o.validity = cd.validity;
     } else {
       if (cd.values && o.values_bytes) {
-        void *h = nullptr;
-        SB_CUDA_CHECK(ctx, cudaMallocHost(&h, o.values_bytes));
-        ow->host_pinned.push_back(h);
-        SB_CUDA_CHECK(ctx, cudaMemcpyAsync(h, cd.values, o.values_bytes, cudaMemcpyDeviceToHost, st));
-        o.values = h;
+        PinnedBlock b;
+        if ((rc = pinned_get(ctx, o.values_bytes, &b))) return rc;
+        ow->host_pinned.push_back(b);
+        SB_CUDA_CHECK(ctx, cudaMemcpyAsync(b.p, cd.values, o.values_bytes, cudaMemcpyDeviceToHost, st));
+        o.values = b.p;
       }
       if (cd.validity && o.validity_bytes) {
-        void *h = nullptr;
-        SB_CUDA_CHECK(ctx, cudaMallocHost(&h, o.validity_bytes));
-        ow->host_pinned.push_back(h);
-        SB_CUDA_CHECK(ctx, cudaMemcpyAsync(h, cd.validity, o.validity_bytes, cudaMemcpyDeviceToHost, st));
-        o.validity = static_cast<uint8_t *>(h);
+        PinnedBlock b;
+        if ((rc = pinned_get(ctx, o.validity_bytes, &b))) return rc;
+        ow->host_pinned.push_back(b);
+        SB_CUDA_CHECK(ctx, cudaMemcpyAsync(b.p, cd.validity, o.validity_bytes, cudaMemcpyDeviceToHost, st));
+        o.validity = static_cast<uint8_t *>(b.p);
       }
     }
   }

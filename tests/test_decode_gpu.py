@@ -151,7 +151,7 @@ def test_boolean(ctx, default):
         roundtrip(ctx, sbo.BOOL, v, validity=val, opts=sbo.make_opts(default))
         roundtrip(ctx, sbo.BOOL, v, validity=val, page_size=1001, opts=sbo.make_opts(default))
     runs = np.repeat(rng.random(200) < 0.5, 50)
-    roundtrip(ctx, sbo.BOOL, runs, opts=sbo.make_opts(default, ratio=2.0), expect_codec="Rle")
+    roundtrip(ctx, sbo.BOOL, np.repeat(rng.random(40) < 0.5, 1000), page_size=8192, opts=sbo.make_opts(default, ratio=2.0), expect_codec="Rle")
     roundtrip(ctx, sbo.BOOL, runs, page_size=777, opts=sbo.make_opts(default, force=sbo.C_RLE), expect_codec="Rle")
     roundtrip(ctx, sbo.BOOL, rng.random(5000) < 0.5, page_size=777, validity=rng.random(5000) > 0.3, opts=sbo.make_opts(default, force=sbo.C_RLE))
 
