@@ -93,7 +93,7 @@ class Decoded:
     """One decoded Arrow array.  Host mode: numpy arrays.  Device mode: raw pointers that stay
     valid until release()."""
 
-    def __init__(self, ctx, type_, out, idx, group):
+    def __init__(self, ctx, type_, out, idx, group, n_nested=0):
         self.type = type_
         self.length = int(out.length)
         self.mem = out.mem
@@ -103,6 +103,11 @@ class Decoded:
         self.offsets_ptr, self.offsets_bytes = out.offsets, int(out.offsets_bytes)
         self.validity_ptr, self.validity_bytes = out.validity, int(out.validity_bytes)
         self.values = self.offsets = self.validity = None
+        # nested leaves: NestedState entries of every depth above the leaf (read_validity_nested)
+        self.nested = []
+        for d in range(max(0, n_nested - 1)):
+            self.nested.append({"len": int(out.nested_len[d]), "offsets_ptr": out.nested_offsets[d],
+                                "validity_ptr": out.nested_validity[d], "offsets": None, "validity": None})
         if out.mem == MEM_HOST:
             def grab(p, n):
                 return np.frombuffer(C.string_at(p, n), dtype=np.uint8).copy() if p and n else (np.zeros(0, np.uint8) if p or n == 0 else None)
@@ -114,6 +119,11 @@ class Decoded:
                 o = grab(out.offsets, self.offsets_bytes)
                 self.offsets = o.view(np.int64 if type_ == LARGE_BINARY else np.int32)
             self.validity = grab(out.validity, self.validity_bytes) if out.validity else None
+            for nd in self.nested:
+                if nd["offsets_ptr"]:
+                    nd["offsets"] = grab(nd["offsets_ptr"], (nd["len"] + 1) * 8).view(np.int64)
+                if nd["validity_ptr"]:
+                    nd["validity"] = grab(nd["validity_ptr"], (nd["len"] + 7) // 8)
 
     def device_view(self, which="values"):
         ptr, n = {"values": (self.values_ptr, self.values_bytes), "offsets": (self.offsets_ptr, self.offsets_bytes),
@@ -204,7 +214,7 @@ class Context:
             _lib.sb_release_columns(self._h, outs, n)
             raise StrawboatError(rc, msg)
         group = _OutGroup(self, outs, n, [len(c.metas) for c in columns])
-        res = [Decoded(self, columns[i].type, outs[i], i, group) for i in range(n)]
+        res = [Decoded(self, columns[i].type, outs[i], i, group, columns[i].leaf.n_nested) for i in range(n)]
         if out == "host":
             group.release()
         return res

@@ -27,17 +27,35 @@ struct PageDesc {
   uint32_t ordinal;    // page index inside its column
   uint64_t out_elem;   // first output element (row / leaf slot) of this page in its column
   uint64_t out_byte;   // binary: first output value byte of this page in its column
+  uint32_t aux;        // index into the PageAux array (binary / nested pages), else 0xffffffff
+  uint32_t last;       // 1 for the last page of its column
+  uint64_t tab_off;    // binary: first BinEntry of this page in the entry table
+};
+
+// Plan-pass results of pages whose output size is data dependent (binary value bytes, nested
+// per-depth entry counts).  Pass 0 writes value_bytes / cnt; the host scans them per column
+// into PageDesc.out_elem / out_byte and base[] before pass 1.
+struct PageAux {
+  uint64_t value_bytes;
+  uint32_t cnt[SB_MAX_NESTED];
+  uint64_t base[SB_MAX_NESTED];
 };
 
 struct ColDesc {
   int32_t type;
-  int32_t nullable;
+  int32_t nullable; // flat: the leaf field is nullable (validity section present)
   int32_t W;        // value width in bytes (primitives), offset width (binary)
   int32_t is_float;
   uint8_t *values;
   uint8_t *offsets;
   uint8_t *validity;
   uint64_t length;  // total elements
+  // nested leaves (n_nested > 1): InitNested root -> leaf and the derived level thresholds
+  int32_t n_nested;
+  uint8_t kind[SB_MAX_NESTED], nnull[SB_MAX_NESTED];
+  uint8_t cum_sum[SB_MAX_NESTED + 1], cum_rep[SB_MAX_NESTED + 1];
+  int64_t *nest_off[SB_MAX_NESTED];
+  uint8_t *nest_val[SB_MAX_NESTED];
 };
 
 struct WorkItem {

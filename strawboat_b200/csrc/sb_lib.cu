@@ -17,6 +17,8 @@
 
 #include "sb_common.cuh"
 #include "sb_decode.cuh"
+#include "sb_binary.cuh"
+#include "sb_nested.cuh"
 
 namespace sb {
 
@@ -68,7 +70,7 @@ __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const Col
   if (i >= n_pages) return;
   const PageDesc pg = pages[i];
   const ColDesc col = cols[pg.col];
-  if (!is_fixed_type(col.type)) return;
+  if (!is_fixed_type(col.type) || col.n_nested > 1) return;
   uint32_t vb, clen;
   if (!lz4_side_page(pg.src, pg.len, col.nullable != 0, &vb, &clen)) return;
   uint32_t slot = atomicAdd(n_jobs, 1u);
@@ -103,12 +105,16 @@ __global__ void __launch_bounds__(kLz4Warps * 32)
 }
 
 // ------------------------------------------------------------------------------------
-// main decode kernel
+// main decode kernel.  pass 0 = plan pass over the pages whose output size is data dependent
+// (binary value bytes, nested per-depth entry counts); pass 1 = decode.
 // ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_binary_type(int t) { return t == SB_BINARY || t == SB_LARGE_BINARY; }
+
 __global__ void __launch_bounds__(SB_NT)
     sb_decode_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols,
                      const WorkItem *__restrict__ items, uint32_t n_items, uint32_t *counter, uint8_t *scratch,
-                     uint64_t scratch_per_cta, int32_t *status, uint32_t stage_cap, uint32_t smem_bytes, const uint8_t *__restrict__ side_flags) {
+                     uint64_t scratch_per_cta, int32_t *status, uint32_t stage_cap, uint32_t smem_bytes,
+                     const uint8_t *__restrict__ side_flags, PageAux *aux, BinEntry *entries, uint32_t *codec_hist, int pass) {
   extern __shared__ __align__(128) uint8_t dsm[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_err;
@@ -134,9 +140,10 @@ __global__ void __launch_bounds__(SB_NT)
     if (it >= n_items) break;
     const WorkItem wi = items[it];
     const PageDesc pg = pages[wi.page];
-    const ColDesc col = cols[pg.col];
-    const bool lz4_side = side_flags != nullptr && side_flags[wi.page] != 0;
+    const ColDesc &col = cols[pg.col];
+    const bool lz4_side = pass == 1 && side_flags != nullptr && side_flags[wi.page] != 0;
     if (lz4_side && !col.nullable) { // value block handled by sb_lz4_kernel, nothing else in the page
+      if (tid == 0 && (wi.tile == 0 || wi.tile == 0xffffffffu)) atomicAdd(codec_hist + SB_C_LZ4, 1u);
       __syncthreads();
       continue;
     }
@@ -174,10 +181,12 @@ __global__ void __launch_bounds__(SB_NT)
     const uint32_t avail = pg.len;
     uint32_t n = pg.num_values;
     bool ok = true;
+    const bool nested = col.n_nested > 1;
+    const bool flat_fixed = is_fixed_type(col.type) && !nested;
 
     if (col.type == SB_NULL) {
       // null.rs: length only, nothing to decode
-    } else if (!staged && wi.tile != 0xffffffffu && is_fixed_type(col.type) && !col.nullable) {
+    } else if (pass == 1 && !staged && wi.tile != 0xffffffffu && flat_fixed && !col.nullable) {
       // ---- oversized page (e.g. max_page_size = None): None / OneValue are split into
       //      tiles that stream straight from global memory; anything else runs on tile 0.
       int codec = avail >= 9 ? int(p[0]) : -1;
@@ -186,6 +195,7 @@ __global__ void __launch_bounds__(SB_NT)
       const uint32_t tile_elems = kTileBytes / W;
       uint32_t lo = min(n, wi.tile * tile_elems), hi = min(n, lo + tile_elems);
       uint8_t *dst = col.values + pg.out_elem * W;
+      if (wi.tile == 0 && tid == 0 && codec >= 0 && codec < 32) atomicAdd(codec_hist + codec, 1u);
       if (codec == SB_C_NONE && avail >= 9 && compressed <= avail - 9 && uint64_t(compressed) == uint64_t(n) * W) {
         copy_bytes(dst + uint64_t(lo) * W, p + 9 + uint64_t(lo) * W, uint64_t(hi - lo) * W);
       } else if (codec == SB_C_ONEVALUE && avail >= 9 + W) {
@@ -200,20 +210,49 @@ __global__ void __launch_bounds__(SB_NT)
         if (!lz4_side) ok = decode_fixed<0>(cx, p, avail, n, col.W, col.is_float != 0, dst, &used);
       }
     } else if (wi.tile == 0 || wi.tile == 0xffffffffu) {
+      PageAux *ax = pg.aux != 0xffffffffu ? aux + pg.aux : nullptr;
       uint32_t vb = 0;
-      if (col.nullable) {
-        vb = decode_validity(cx, p, avail, n, col.validity, pg.out_elem);
+      uint64_t out_elem = pg.out_elem;
+      if (nested) {
+        // levels section: NestedState entries + leaf validity; n becomes the leaf slot count
+        uint32_t leaf_len = 0;
+        vb = decode_levels(cx, p, avail, n, col, pass, ax, pg.last != 0, &leaf_len);
+        if (vb == 0xffffffffu) ok = false;
+        n = leaf_len;
+      } else if (col.nullable) {
+        if (pass == 1) {
+          vb = decode_validity(cx, p, avail, n, col.validity, pg.out_elem);
+        } else { // plan pass: only skip the section
+          uint32_t L = avail >= 4 ? ld_u32u(p) : 0xffffffffu;
+          vb = (avail >= 4 && L <= avail - 4) ? 4 + L : 0xffffffffu;
+          if (vb == 0xffffffffu) cx.flag(SB_IO);
+        }
         if (vb == 0xffffffffu) ok = false;
       }
-      if (ok) {
+      if (ok && pass == 1 && tid == 0 && avail > vb && p[vb] < 32) atomicAdd(codec_hist + p[vb], 1u);
+      if (ok && pass == 0) {
+        if (is_binary_type(col.type)) {
+          uint64_t vbytes = 0;
+          ok = binary_page_size(cx, p, avail, vb, n, entries + pg.tab_off, &vbytes);
+          if (tid == 0) ax->value_bytes = ok ? vbytes : 0;
+        } else if (tid == 0) {
+          ax->value_bytes = 0;
+        }
+      } else if (ok) {
         if (col.type == SB_BOOL) {
-          ok = decode_boolean(cx, p + vb, avail - vb, n, col.values, pg.out_elem);
+          ok = decode_boolean(cx, p + vb, avail - vb, n, col.values, out_elem);
         } else if (is_fixed_type(col.type)) {
           uint32_t used = 0;
           // top-level LZ4 blocks are decoded by sb_lz4_kernel (same predicate as sb_classify_kernel)
           if (!lz4_side)
             ok = decode_fixed<0>(cx, p + vb, avail - vb, n, col.W, col.is_float != 0,
-                                 col.values + pg.out_elem * uint64_t(col.W), &used);
+                                 col.values + out_elem * uint64_t(col.W), &used);
+        } else if (col.type == SB_BINARY) {
+          ok = decode_binary<4>(cx, p, avail, vb, n, reinterpret_cast<int32_t *>(col.offsets) + out_elem,
+                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off);
+        } else if (col.type == SB_LARGE_BINARY) {
+          ok = decode_binary<8>(cx, p, avail, vb, n, reinterpret_cast<int64_t *>(col.offsets) + out_elem,
+                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off);
         } else {
           cx.flag(SB_NYI);
         }
@@ -258,7 +297,7 @@ struct sb_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
   int sm_count = 0;
   int max_smem_optin = 0;
-  DevBuf d_tables, d_scratch;
+  DevBuf d_tables, d_scratch, d_entries;
   void *h_tables = nullptr;
   size_t h_tables_cap = 0;
   std::vector<PinnedBlock> pinned_free; // pinned host blocks are expensive to create: recycled
@@ -385,7 +424,7 @@ void sb_ctx_destroy(sb_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->aux);
-  for (DevBuf *b : {&ctx->d_tables, &ctx->d_scratch})
+  for (DevBuf *b : {&ctx->d_tables, &ctx->d_scratch, &ctx->d_entries})
     if (b->p) cudaFreeAsync(b->p, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
@@ -437,17 +476,23 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   ctx->stats = sb_stats{};
 
   // ---- host pass: validate, count pages / work items
-  uint64_t n_pages_total = 0, n_items = 0, max_elems_bytes = 0;
+  uint64_t n_pages_total = 0, n_items = 0, n_plan = 0, n_entries = 0, max_elems_bytes = 0;
   uint32_t max_stage = 0;
   const uint32_t stage_cap = kSmemMax - kArenaMin;
+  auto col_binary = [](const sb_column_in &ci) { return ci.leaf.type == SB_BINARY || ci.leaf.type == SB_LARGE_BINARY; };
+  auto col_nested = [](const sb_column_in &ci) { return ci.leaf.n_nested > 1; };
   for (uint64_t c = 0; c < n_cols; ++c) {
     const sb_column_in &ci = cols[c];
     if (ci.leaf.type < SB_NULL || ci.leaf.type > SB_LARGE_BINARY) return fail(ctx, SB_NYI, "unsupported physical type");
-    if (ci.leaf.n_nested > 1) return fail(ctx, SB_NYI, "nested leaves: not implemented yet");
-    if (ci.leaf.type == SB_BINARY || ci.leaf.type == SB_LARGE_BINARY) return fail(ctx, SB_NYI, "binary leaves: not implemented yet");
+    if (ci.leaf.n_nested > SB_MAX_NESTED) return fail(ctx, SB_NYI, "nesting deeper than SB_MAX_NESTED");
+    if (col_nested(ci)) {
+      if (ci.leaf.nested_kind[ci.leaf.n_nested - 1] != SB_N_PRIMITIVE) return fail(ctx, SB_INVALID_ARG, "the last nested entry must be the primitive leaf");
+      if (ci.leaf.type == SB_NULL) return fail(ctx, SB_NYI, "nested Null leaves");
+    }
     if (ci.n_pages && !ci.metas) return fail(ctx, SB_INVALID_ARG, "metas is NULL");
     if (ci.nbytes && !ci.bytes) return fail(ctx, SB_INVALID_ARG, "bytes is NULL");
     n_pages_total += ci.n_pages;
+    const bool plan = col_binary(ci) || col_nested(ci);
     const uint64_t W = std::max(1, type_width(ci.leaf.type));
     for (uint64_t p = 0; p < ci.n_pages; ++p) {
       const sb_page_meta &m = ci.metas[p];
@@ -457,9 +502,11 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
         max_stage = std::max<uint32_t>(max_stage, uint32_t(m.length));
       } else {
         uint64_t out_bytes = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * W;
-        bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type);
+        bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type) && !col_nested(ci);
         n_items += tiled ? std::max<uint64_t>(1, (out_bytes + kTileBytes - 1) / kTileBytes) : 1;
       }
+      if (plan) n_plan += 1;
+      if (col_binary(ci)) n_entries += m.length / 8 + 1;
       max_elems_bytes = std::max<uint64_t>(max_elems_bytes, m.num_values * std::max<uint64_t>(W, 4));
     }
   }
@@ -468,30 +515,62 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     for (uint64_t c = 0; c < n_cols; ++c) outs[c]._owner = owners[c];
     sb_release_columns(ctx, outs, n_cols);
   };
+#define SB_TRY(call)            \
+  do {                          \
+    int rc__ = (call);          \
+    if (rc__ != SB_OK) {        \
+      cleanup();                \
+      return rc__;              \
+    }                           \
+  } while (0)
+#define SB_TRY_CUDA(call)                                                                      \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      cleanup();                                                                               \
+      return fail(ctx, SB_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    }                                                                                          \
+  } while (0)
 
   // one pinned staging buffer, mirrored on the device:
-  //   uploaded : [ColDesc * n_cols][PageDesc * P][WorkItem * I]
-  //   zeroed   : [status * P][counters * 4][side_flags * P]      device only: [Lz4Job * P]
+  //   uploaded : [ColDesc * n_cols][PageDesc * P][WorkItem * I][WorkItem * plan][PageAux * plan]
+  //   zeroed   : [status * P][counters * 36][side_flags * P]      device only: [Lz4Job * P]
   size_t off_cols = 0;
   size_t off_pages = align_up(off_cols + sizeof(ColDesc) * n_cols, 16);
   size_t off_items = align_up(off_pages + sizeof(PageDesc) * n_pages_total, 16);
-  size_t tables_bytes = align_up(off_items + sizeof(WorkItem) * n_items, 16);
+  size_t off_items0 = align_up(off_items + sizeof(WorkItem) * n_items, 16);
+  size_t off_aux = align_up(off_items0 + sizeof(WorkItem) * n_plan, 16);
+  size_t tables_bytes = align_up(off_aux + sizeof(PageAux) * n_plan, 16);
   size_t off_status = tables_bytes;
   size_t off_counters = align_up(off_status + sizeof(int32_t) * n_pages_total, 16);
-  size_t off_flags = off_counters + 16;
+  size_t off_flags = off_counters + 36 * 4;
   size_t zero_end = align_up(off_flags + n_pages_total, 16);
   size_t off_jobs = zero_end;
   size_t dev_bytes = off_jobs + sizeof(Lz4Job) * n_pages_total;
   int rc;
   if ((rc = host_tables_reserve(ctx, zero_end))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_tables, dev_bytes))) return rc;
+  if (n_entries && (rc = dev_reserve(ctx, ctx->d_entries, n_entries * sizeof(BinEntry)))) return rc;
   uint8_t *hT = static_cast<uint8_t *>(ctx->h_tables);
   uint8_t *dT = static_cast<uint8_t *>(ctx->d_tables.p);
   ColDesc *h_cols = reinterpret_cast<ColDesc *>(hT + off_cols);
   PageDesc *h_pages = reinterpret_cast<PageDesc *>(hT + off_pages);
   WorkItem *h_items = reinterpret_cast<WorkItem *>(hT + off_items);
+  WorkItem *h_items0 = reinterpret_cast<WorkItem *>(hT + off_items0);
+  PageAux *h_aux = reinterpret_cast<PageAux *>(hT + off_aux);
+  std::memset(h_aux, 0, sizeof(PageAux) * n_plan);
 
-  uint64_t pi = 0, ii = 0, bytes_in = 0, bytes_out = 0;
+  // device allocation of an output buffer, owned by the column
+  auto dev_out = [&](Owner *ow, uint64_t bytes, bool zero, uint8_t **out) -> int {
+    void *d = nullptr;
+    SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, bytes + 16, st));
+    ow->dev.push_back(d);
+    if (zero) SB_CUDA_CHECK(ctx, cudaMemsetAsync(d, 0, bytes + 16, st));
+    *out = static_cast<uint8_t *>(d);
+    return SB_OK;
+  };
+
+  uint64_t pi = 0, ii = 0, i0 = 0, ent = 0, bytes_in = 0, bytes_out = 0;
   std::vector<void *> d_inputs; // device copies of host inputs, freed at the end of the call
   bool any_fixed = false;
   for (uint64_t c = 0; c < n_cols; ++c) {
@@ -499,7 +578,8 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     Owner *ow = new Owner();
     owners[c] = ow;
     const int W = type_width(ci.leaf.type);
-    any_fixed |= fixed_type(ci.leaf.type);
+    const bool nested = col_nested(ci), binary = col_binary(ci);
+    any_fixed |= fixed_type(ci.leaf.type) && !nested;
     uint64_t rows = 0, total_len = 0;
     for (uint64_t p = 0; p < ci.n_pages; ++p) {
       rows += ci.metas[p].num_values;
@@ -513,46 +593,48 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     const uint8_t *d_in = ci.bytes;
     if (ci.mem == SB_MEM_HOST && total_len) {
       void *d = nullptr;
-      SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, align_up(total_len + 32, 256), st));
+      SB_TRY_CUDA(cudaMallocAsync(&d, align_up(total_len + 32, 256), st));
       d_inputs.push_back(d);
-      SB_CUDA_CHECK(ctx, cudaMemcpyAsync(d, ci.bytes, total_len, cudaMemcpyHostToDevice, st));
+      SB_TRY_CUDA(cudaMemcpyAsync(d, ci.bytes, total_len, cudaMemcpyHostToDevice, st));
       d_in = static_cast<const uint8_t *>(d);
     }
-    // outputs
+    // outputs whose size is known up front (flat columns; binary value bytes come later)
     sb_column_out &o = outs[c];
-    o.length = rows;
     o.mem = out_mem;
     ColDesc &cd = h_cols[c];
     std::memset(&cd, 0, sizeof(cd));
     cd.type = ci.leaf.type;
-    cd.nullable = ci.leaf.nullable != 0 && ci.leaf.type != SB_NULL;
+    cd.nullable = !nested && ci.leaf.nullable != 0 && ci.leaf.type != SB_NULL;
     cd.W = W;
     cd.is_float = ci.leaf.type == SB_F32 || ci.leaf.type == SB_F64;
-    cd.length = rows;
-    uint64_t bitmap_bytes = align_up((rows + 7) / 8, 4);
-    if (ci.leaf.type == SB_BOOL) {
-      o.values_bytes = (rows + 7) / 8;
-      void *d = nullptr;
-      SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, bitmap_bytes + 16, st));
-      ow->dev.push_back(d);
-      SB_CUDA_CHECK(ctx, cudaMemsetAsync(d, 0, bitmap_bytes + 16, st));
-      cd.values = static_cast<uint8_t *>(d);
-    } else if (W && ci.leaf.type != SB_NULL) {
-      o.values_bytes = rows * uint64_t(W);
-      void *d = nullptr;
-      SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, o.values_bytes + 16, st));
-      ow->dev.push_back(d);
-      cd.values = static_cast<uint8_t *>(d);
+    cd.n_nested = nested ? ci.leaf.n_nested : 0;
+    if (nested) {
+      for (int d = 0; d < ci.leaf.n_nested; ++d) {
+        cd.kind[d] = uint8_t(ci.leaf.nested_kind[d]);
+        cd.nnull[d] = ci.leaf.nested_nullable[d] != 0;
+        cd.cum_sum[d + 1] = uint8_t(cd.cum_sum[d] + cd.nnull[d] + (cd.kind[d] == SB_N_LIST));
+        cd.cum_rep[d + 1] = uint8_t(cd.cum_rep[d] + (cd.kind[d] == SB_N_LIST));
+      }
+    } else {
+      o.length = rows;
+      cd.length = rows;
+      uint64_t bitmap_bytes = align_up((rows + 7) / 8, 4);
+      if (ci.leaf.type == SB_BOOL) {
+        o.values_bytes = (rows + 7) / 8;
+        SB_TRY(dev_out(ow, bitmap_bytes, true, &cd.values));
+      } else if (binary) {
+        o.offsets_bytes = (rows + 1) * uint64_t(W);
+        SB_TRY(dev_out(ow, o.offsets_bytes, false, &cd.offsets));
+        SB_TRY_CUDA(cudaMemsetAsync(cd.offsets, 0, size_t(W), st)); // offsets[0] = 0 even for a column without pages
+      } else if (W && ci.leaf.type != SB_NULL) {
+        o.values_bytes = rows * uint64_t(W);
+        SB_TRY(dev_out(ow, o.values_bytes, false, &cd.values));
+      }
+      if (cd.nullable) {
+        o.validity_bytes = (rows + 7) / 8;
+        SB_TRY(dev_out(ow, bitmap_bytes, true, &cd.validity));
+      }
     }
-    if (cd.nullable) {
-      o.validity_bytes = (rows + 7) / 8;
-      void *d = nullptr;
-      SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, bitmap_bytes + 16, st));
-      ow->dev.push_back(d);
-      SB_CUDA_CHECK(ctx, cudaMemsetAsync(d, 0, bitmap_bytes + 16, st));
-      cd.validity = static_cast<uint8_t *>(d);
-    }
-    bytes_out += o.values_bytes + o.validity_bytes;
     // pages
     uint64_t src_off = 0, elem = 0;
     for (uint64_t p = 0; p < ci.n_pages; ++p) {
@@ -565,11 +647,22 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       pd.ordinal = uint32_t(p);
       pd.out_elem = elem;
       pd.out_byte = 0;
+      pd.aux = 0xffffffffu;
+      pd.last = p + 1 == ci.n_pages;
+      pd.tab_off = 0;
+      if (binary || nested) {
+        pd.aux = uint32_t(i0);
+        h_items0[i0++] = WorkItem{uint32_t(pi), 0xffffffffu};
+      }
+      if (binary) {
+        pd.tab_off = ent;
+        ent += m.length / 8 + 1;
+      }
       if (m.length + 32 <= stage_cap) {
         h_items[ii++] = WorkItem{uint32_t(pi), 0xffffffffu};
       } else {
         uint64_t out_b = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * uint64_t(std::max(1, W));
-        bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type);
+        bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type) && !nested;
         uint64_t nt = tiled ? std::max<uint64_t>(1, (out_b + kTileBytes - 1) / kTileBytes) : 1;
         for (uint64_t t = 0; t < nt; ++t) h_items[ii++] = WorkItem{uint32_t(pi), uint32_t(t)};
       }
@@ -580,80 +673,165 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     }
   }
 
-  // ---- launch
+  // ---- launch configuration
   uint32_t smem = uint32_t(align_up(std::min<uint64_t>(uint64_t(max_stage) + 48, stage_cap) + kArenaMin, 1024));
   smem = std::min(std::max(smem, kSmemMin), kSmemMax);
   int occ = 1;
-  SB_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_decode_kernel, SB_NT, smem));
+  SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_decode_kernel, SB_NT, smem));
   occ = std::max(1, occ);
-  uint32_t grid = uint32_t(std::min<uint64_t>(n_items, uint64_t(ctx->sm_count) * occ));
+  uint32_t grid = uint32_t(std::min<uint64_t>(std::max<uint64_t>(n_items, 1), uint64_t(ctx->sm_count) * occ));
   uint64_t scratch_per_cta = align_up(3 * (max_elems_bytes + 64) + 16 * 1024, 256);
+  const PageDesc *d_pages = reinterpret_cast<const PageDesc *>(dT + off_pages);
+  const ColDesc *d_cols = reinterpret_cast<const ColDesc *>(dT + off_cols);
+  int32_t *d_status = reinterpret_cast<int32_t *>(dT + off_status);
+  // counters: [0] main queue, [1] lz4 queue, [2] n lz4 jobs, [3] plan queue, [4..35] pages per top-level codec
+  uint32_t *d_counters = reinterpret_cast<uint32_t *>(dT + off_counters);
+  uint8_t *d_flags = dT + off_flags;
+  Lz4Job *d_jobs = reinterpret_cast<Lz4Job *>(dT + off_jobs);
+  PageAux *d_aux = reinterpret_cast<PageAux *>(dT + off_aux);
+  BinEntry *d_entries = static_cast<BinEntry *>(ctx->d_entries.p);
   if (n_items) {
-    if ((rc = dev_reserve(ctx, ctx->d_scratch, scratch_per_cta * grid))) {
-      cleanup();
-      return rc;
+    SB_TRY(dev_reserve(ctx, ctx->d_scratch, scratch_per_cta * grid));
+    SB_TRY_CUDA(cudaMemcpyAsync(dT, hT, tables_bytes, cudaMemcpyHostToDevice, st));
+    SB_TRY_CUDA(cudaMemsetAsync(dT + off_status, 0, zero_end - off_status, st));
+    SB_TRY_CUDA(cudaEventRecord(ctx->ev0, st));
+  }
+
+  // ---- pass 0 (plan): sizes of binary / nested pages, then the host lays out their outputs
+  if (n_plan) {
+    uint32_t grid0 = uint32_t(std::min<uint64_t>(n_plan, uint64_t(ctx->sm_count) * occ));
+    sb_decode_kernel<<<grid0, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items0), uint32_t(n_plan),
+                                                 d_counters + 3, static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta, d_status,
+                                                 stage_cap, smem, nullptr, d_aux, d_entries, d_counters + 4, 0);
+    SB_TRY_CUDA(cudaGetLastError());
+    ctx->stats.kernel_launches += 1;
+    SB_TRY_CUDA(cudaMemcpyAsync(h_aux, d_aux, sizeof(PageAux) * n_plan, cudaMemcpyDeviceToHost, st));
+    SB_TRY_CUDA(cudaStreamSynchronize(st));
+    pi = 0;
+    for (uint64_t c = 0; c < n_cols; ++c) {
+      const sb_column_in &ci = cols[c];
+      const bool nested = col_nested(ci), binary = col_binary(ci);
+      if (!nested && !binary) {
+        pi += ci.n_pages;
+        continue;
+      }
+      Owner *ow = owners[c];
+      sb_column_out &o = outs[c];
+      ColDesc &cd = h_cols[c];
+      const int D = nested ? ci.leaf.n_nested : 0;
+      uint64_t base[SB_MAX_NESTED] = {0}, vbytes = 0;
+      for (uint64_t p = 0; p < ci.n_pages; ++p, ++pi) {
+        PageDesc &pd = h_pages[pi];
+        PageAux &ax = h_aux[pd.aux];
+        pd.out_byte = vbytes;
+        vbytes += ax.value_bytes;
+        if (nested) {
+          pd.out_elem = base[D - 1];
+          for (int d = 0; d < D; ++d) {
+            ax.base[d] = base[d];
+            base[d] += ax.cnt[d];
+          }
+        }
+      }
+      if (nested) {
+        const uint64_t rows = base[D - 1]; // leaf slots
+        const int W = type_width(ci.leaf.type);
+        o.length = rows;
+        cd.length = rows;
+        const uint64_t bitmap_bytes = align_up((rows + 7) / 8, 4);
+        if (ci.leaf.type == SB_BOOL) {
+          o.values_bytes = (rows + 7) / 8;
+          SB_TRY(dev_out(ow, bitmap_bytes, true, &cd.values));
+        } else if (binary) {
+          o.offsets_bytes = (rows + 1) * uint64_t(W);
+          SB_TRY(dev_out(ow, o.offsets_bytes, false, &cd.offsets));
+          SB_TRY_CUDA(cudaMemsetAsync(cd.offsets, 0, size_t(W), st));
+        } else {
+          o.values_bytes = rows * uint64_t(W);
+          SB_TRY(dev_out(ow, o.values_bytes, false, &cd.values));
+        }
+        if (cd.nnull[D - 1]) {
+          o.validity_bytes = (rows + 7) / 8;
+          SB_TRY(dev_out(ow, bitmap_bytes, true, &cd.validity));
+        }
+        for (int d = 0; d + 1 < D; ++d) {
+          o.nested_len[d] = base[d];
+          if (cd.kind[d] == SB_N_LIST) {
+            uint8_t *q = nullptr;
+            SB_TRY(dev_out(ow, (base[d] + 1) * 8, ci.n_pages == 0, &q));
+            cd.nest_off[d] = reinterpret_cast<int64_t *>(q);
+          }
+          if (cd.nnull[d]) SB_TRY(dev_out(ow, align_up((base[d] + 7) / 8, 4), true, &cd.nest_val[d]));
+        }
+      }
+      if (binary) {
+        o.values_bytes = vbytes;
+        SB_TRY(dev_out(ow, vbytes, false, &cd.values));
+      }
     }
-    SB_CUDA_CHECK(ctx, cudaMemcpyAsync(dT, hT, tables_bytes, cudaMemcpyHostToDevice, st));
-    SB_CUDA_CHECK(ctx, cudaMemsetAsync(dT + off_status, 0, zero_end - off_status, st));
-    const PageDesc *d_pages = reinterpret_cast<const PageDesc *>(dT + off_pages);
-    const ColDesc *d_cols = reinterpret_cast<const ColDesc *>(dT + off_cols);
-    int32_t *d_status = reinterpret_cast<int32_t *>(dT + off_status);
-    uint32_t *d_counters = reinterpret_cast<uint32_t *>(dT + off_counters); // [0] main queue, [1] lz4 queue, [2] n lz4 jobs
-    uint8_t *d_flags = dT + off_flags;
-    Lz4Job *d_jobs = reinterpret_cast<Lz4Job *>(dT + off_jobs);
-    SB_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, st));
+    SB_TRY_CUDA(cudaMemcpyAsync(dT, hT, tables_bytes, cudaMemcpyHostToDevice, st));
+  }
+
+  // ---- pass 1 (decode)
+  if (n_items) {
     if (any_fixed) {
       // D0: find top-level LZ4 blocks; run them warp-per-page next to the main kernel
       sb_classify_kernel<<<uint32_t((n_pages_total + 255) / 256), 256, 0, st>>>(d_pages, d_cols, uint32_t(n_pages_total), d_jobs,
                                                                               d_counters + 2, d_flags);
-      SB_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_fork, st));
-      SB_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+      SB_TRY_CUDA(cudaEventRecord(ctx->ev_fork, st));
+      SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
       int lz4_occ = 1;
-      SB_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz4_occ, sb_lz4_kernel, kLz4Warps * 32, 0));
+      SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz4_occ, sb_lz4_kernel, kLz4Warps * 32, 0));
       uint32_t lz4_grid = uint32_t(std::min<uint64_t>((n_pages_total + kLz4Warps - 1) / kLz4Warps,
                                                       uint64_t(ctx->sm_count) * std::max(1, lz4_occ)));
       sb_lz4_kernel<<<lz4_grid, kLz4Warps * 32, 0, ctx->aux>>>(d_jobs, d_counters + 2, d_counters + 1, d_status);
-      SB_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_join, ctx->aux));
+      SB_TRY_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
       ctx->stats.kernel_launches += 2;
     }
     sb_decode_kernel<<<grid, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items),
                                                 uint32_t(n_items), d_counters, static_cast<uint8_t *>(ctx->d_scratch.p),
-                                                scratch_per_cta, d_status, stage_cap, smem, any_fixed ? d_flags : nullptr);
-    SB_CUDA_CHECK(ctx, cudaGetLastError());
-    if (any_fixed) SB_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    SB_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, st));
+                                                scratch_per_cta, d_status, stage_cap, smem, any_fixed ? d_flags : nullptr, d_aux,
+                                                d_entries, d_counters + 4, 1);
+    SB_TRY_CUDA(cudaGetLastError());
+    if (any_fixed) SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    SB_TRY_CUDA(cudaEventRecord(ctx->ev1, st));
     ctx->stats.kernel_launches += 1;
-    // statuses back (pinned), reuse the tail of the host table buffer
-    SB_CUDA_CHECK(ctx, cudaMemcpyAsync(hT + off_status, dT + off_status, sizeof(int32_t) * n_pages_total, cudaMemcpyDeviceToHost, st));
+    // statuses + codec histogram back (pinned), reuse the tail of the host table buffer
+    SB_TRY_CUDA(cudaMemcpyAsync(hT + off_status, dT + off_status, off_flags - off_status, cudaMemcpyDeviceToHost, st));
   }
 
   // ---- results to the caller
+  auto to_caller = [&](Owner *ow, const void *dev, uint64_t bytes, void **out) -> int {
+    if (!dev) return SB_OK;
+    if (out_mem == SB_MEM_DEVICE) {
+      *out = const_cast<void *>(dev);
+      return SB_OK;
+    }
+    PinnedBlock b;
+    int r = pinned_get(ctx, bytes, &b);
+    if (r) return r;
+    ow->host_pinned.push_back(b);
+    if (bytes) SB_CUDA_CHECK(ctx, cudaMemcpyAsync(b.p, dev, bytes, cudaMemcpyDeviceToHost, st));
+    *out = b.p;
+    return SB_OK;
+  };
   for (uint64_t c = 0; c < n_cols; ++c) {
     sb_column_out &o = outs[c];
     Owner *ow = owners[c];
     const ColDesc &cd = h_cols[c];
-    if (out_mem == SB_MEM_DEVICE) {
-      o.values = cd.values;
-      o.validity = cd.validity;
-    } else {
-      if (cd.values && o.values_bytes) {
-        PinnedBlock b;
-        if ((rc = pinned_get(ctx, o.values_bytes, &b))) return rc;
-        ow->host_pinned.push_back(b);
-        SB_CUDA_CHECK(ctx, cudaMemcpyAsync(b.p, cd.values, o.values_bytes, cudaMemcpyDeviceToHost, st));
-        o.values = b.p;
-      }
-      if (cd.validity && o.validity_bytes) {
-        PinnedBlock b;
-        if ((rc = pinned_get(ctx, o.validity_bytes, &b))) return rc;
-        ow->host_pinned.push_back(b);
-        SB_CUDA_CHECK(ctx, cudaMemcpyAsync(b.p, cd.validity, o.validity_bytes, cudaMemcpyDeviceToHost, st));
-        o.validity = static_cast<uint8_t *>(b.p);
-      }
+    SB_TRY(to_caller(ow, cd.values, o.values_bytes, &o.values));
+    SB_TRY(to_caller(ow, cd.offsets, o.offsets_bytes, &o.offsets));
+    SB_TRY(to_caller(ow, cd.validity, o.validity_bytes, reinterpret_cast<void **>(&o.validity)));
+    for (int d = 0; d + 1 < cd.n_nested; ++d) {
+      SB_TRY(to_caller(ow, cd.nest_off[d], (o.nested_len[d] + 1) * 8, reinterpret_cast<void **>(&o.nested_offsets[d])));
+      SB_TRY(to_caller(ow, cd.nest_val[d], (o.nested_len[d] + 7) / 8, reinterpret_cast<void **>(&o.nested_validity[d])));
     }
+    bytes_out += o.values_bytes + o.offsets_bytes + o.validity_bytes;
+    for (int d = 0; d + 1 < cd.n_nested; ++d)
+      bytes_out += (cd.nest_off[d] ? (o.nested_len[d] + 1) * 8 : 0) + (cd.nest_val[d] ? (o.nested_len[d] + 7) / 8 : 0);
   }
   for (void *d : d_inputs) cudaFreeAsync(d, st);
-  SB_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  SB_TRY_CUDA(cudaStreamSynchronize(st));
   if (out_mem == SB_MEM_HOST) { // device copies no longer needed
     for (uint64_t c = 0; c < n_cols; ++c) {
       for (void *p : owners[c]->dev) cudaFreeAsync(p, st);
@@ -664,6 +842,9 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
 
   int32_t first_err = SB_OK;
   const int32_t *h_status = reinterpret_cast<const int32_t *>(hT + off_status);
+  const uint32_t *h_counters = reinterpret_cast<const uint32_t *>(hT + off_counters);
+  if (n_items)
+    for (int i = 0; i < 32; ++i) ctx->stats.codec_pages[i] = h_counters[4 + i];
   pi = 0;
   for (uint64_t c = 0; c < n_cols; ++c) {
     sb_column_out &o = outs[c];
@@ -683,6 +864,8 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   ctx->stats.bytes_in = bytes_in;
   ctx->stats.bytes_out = bytes_out;
   return first_err;
+#undef SB_TRY
+#undef SB_TRY_CUDA
 }
 
 int32_t sb_decode_pages(sb_ctx *ctx, const sb_column_in *pages, uint64_t n_pages, int32_t out_mem, sb_column_out *outs) {

@@ -1,0 +1,143 @@
+"""GPU parity for Binary / Utf8 / LargeBinary value blocks (src/compression/binary/*,
+src/read/array/binary.rs): strawboat_b200 decode == oracle decode, bit for bit."""
+import numpy as np
+import pytest
+import sbo
+from helpers import assert_same, oracle_decode_column, oracle_encode_column
+
+import strawboat_b200 as sb
+from strawboat_b200.workloads import random_strings
+
+pytestmark = pytest.mark.gpu
+
+
+def roundtrip(ctx, type_, values, validity=None, nullable=None, page_size=2048, opts=None, expect_codec=None):
+    if nullable is None:
+        nullable = validity is not None
+    data, metas = oracle_encode_column(type_, values, validity, nullable, page_size, opts)
+    if expect_codec is not None:
+        tree = sbo.stat_page(type_, nullable, data[:metas[0][0]])
+        assert tree.startswith(expect_codec), tree
+    ref = oracle_decode_column(type_, nullable, data, metas)
+    dec = ctx.batch_read_array(sb.Column(type_, nullable, data, metas))
+    assert_same(dec, ref, type_, nullable)
+    return dec
+
+
+def strings(rng, n, uniq, nulls=0.0, large=False, maxlen=None):
+    if maxlen is None:
+        o, d, v = random_strings(rng, n, uniq, nulls, large=large)
+        return (o, d), v
+    lens = rng.integers(0, maxlen + 1, n)
+    offsets = np.zeros(n + 1, dtype=np.int64 if large else np.int32)
+    np.cumsum(lens, out=offsets[1:])
+    data = rng.integers(0, 256, int(offsets[-1])).astype(np.uint8)
+    v = (rng.random(n) >= nulls) if nulls else None
+    return (offsets, data), v
+
+
+@pytest.mark.parametrize("type_", [sbo.BINARY, sbo.LARGE_BINARY])
+@pytest.mark.parametrize("default", [sbo.C_NONE, sbo.C_LZ4])
+def test_basic(ctx, type_, default):
+    """new_test_chunk utf8 columns + random binary (io.rs:48-102)."""
+    large = type_ == sbo.LARGE_BINARY
+    odt = np.int64 if large else np.int32
+    words = [b"a", b"bbbbb", b"", b"cc", b"dddddddd", b"e"]
+    off = np.cumsum([0] + [len(w) for w in words]).astype(odt)
+    dat = np.frombuffer(b"".join(words), np.uint8)
+    roundtrip(ctx, type_, (off, dat), opts=sbo.make_opts(default))
+    rng = np.random.default_rng(1)
+    for n in (1, 100, 5000):
+        vals, _ = strings(rng, n, None, large=large, maxlen=40)
+        roundtrip(ctx, type_, vals, opts=sbo.make_opts(default))
+        vals, v = strings(rng, n, None, nulls=0.3, large=large, maxlen=40)
+        roundtrip(ctx, type_, vals, validity=v, opts=sbo.make_opts(default))
+        roundtrip(ctx, type_, vals, validity=v, page_size=777, opts=sbo.make_opts(default))
+
+
+@pytest.mark.parametrize("type_", [sbo.BINARY, sbo.LARGE_BINARY])
+@pytest.mark.parametrize("force", [sbo.C_DICT, sbo.C_FREQ, sbo.C_ONEVALUE])
+def test_forced(ctx, type_, force):
+    large = type_ == sbo.LARGE_BINARY
+    rng = np.random.default_rng(2)
+    for uniq in (1, 8, 1000):
+        for nulls in (0.0, 0.4):
+            if force == sbo.C_ONEVALUE and uniq != 1:
+                continue
+            vals, v = strings(rng, 6000, uniq, nulls=nulls, large=large)
+            for default in (sbo.C_NONE, sbo.C_LZ4):
+                roundtrip(ctx, type_, vals, validity=v, opts=sbo.make_opts(default, ratio=2.0, force=force))
+
+
+@pytest.mark.parametrize("type_", [sbo.BINARY, sbo.LARGE_BINARY])
+def test_adaptive(ctx, type_):
+    """config 3 shapes: low-cardinality decimal strings, 40 % nulls, adaptive on."""
+    large = type_ == sbo.LARGE_BINARY
+    rng = np.random.default_rng(3)
+    opts = sbo.make_opts(sbo.C_LZ4, ratio=2.0)
+    vals, v = strings(rng, 8192 * 3 + 55, 1000, nulls=0.4, large=large)
+    roundtrip(ctx, type_, vals, validity=v, page_size=8192, opts=opts, expect_codec="Dict")
+    vals, v = strings(rng, 8192 * 2, 1, large=large)
+    roundtrip(ctx, type_, vals, page_size=8192, opts=opts, expect_codec="OneValue")
+    # sorted within the page: the Dict index sub-page picks RLE ("dict+RLE")
+    o, d, v = random_strings(rng, 8192 * 2, 100, 0.0, large=large, sort_within=8192)
+    roundtrip(ctx, type_, (o, d), page_size=8192, opts=opts, expect_codec="Dict(Rle")
+    # 95 % one value: Freq
+    n = 8192
+    ids = np.where(rng.random(n) < 0.95, 0, rng.integers(1, 500, n))
+    table = [b"the-frequent-value"] + [b"x%d" % i for i in range(1, 500)]
+    lens = np.array([len(table[i]) for i in ids])
+    off = np.zeros(n + 1, np.int64 if large else np.int32)
+    np.cumsum(lens, out=off[1:])
+    dat = np.frombuffer(b"".join(table[i] for i in ids), np.uint8)
+    roundtrip(ctx, type_, (off, dat), page_size=8192, opts=opts, expect_codec="Freq")
+    # high-cardinality random bytes: falls back to the default codec
+    vals, v = strings(rng, 5000, None, nulls=0.1, large=large, maxlen=24)
+    roundtrip(ctx, type_, vals, validity=v, page_size=2048, opts=opts)
+
+
+def test_empty_and_long_values(ctx):
+    rng = np.random.default_rng(4)
+    n = 300
+    off = np.zeros(n + 1, np.int32)
+    roundtrip(ctx, sbo.BINARY, (off, np.zeros(0, np.uint8)))  # all empty strings
+    lens = np.where(rng.random(n) < 0.05, rng.integers(1000, 20000, n), rng.integers(0, 5, n))
+    off = np.zeros(n + 1, np.int32)
+    np.cumsum(lens, out=off[1:])
+    dat = rng.integers(0, 256, int(off[-1])).astype(np.uint8)
+    for opts in (sbo.make_opts(), sbo.make_opts(sbo.C_LZ4), sbo.make_opts(force=sbo.C_DICT), sbo.make_opts(force=sbo.C_FREQ)):
+        roundtrip(ctx, sbo.BINARY, (off, dat), page_size=100, opts=opts)
+        roundtrip(ctx, sbo.BINARY, (off, dat), page_size=None, opts=opts)
+
+
+def test_binary_with_other_columns(ctx):
+    rng = np.random.default_rng(5)
+    cols, refs = [], []
+    for i, t in enumerate([sbo.BINARY, sbo.I64, sbo.LARGE_BINARY, sbo.BOOL, sbo.BINARY]):
+        n = 4000 + 13 * i
+        if t in (sbo.BINARY, sbo.LARGE_BINARY):
+            vals, v = strings(rng, n, 50, nulls=0.2 if i else 0.0, large=t == sbo.LARGE_BINARY)
+        elif t == sbo.BOOL:
+            vals, v = rng.random(n) < 0.5, None
+        else:
+            vals, v = rng.integers(0, 100, n).astype(np.int64), rng.random(n) > 0.1
+        data, metas = oracle_encode_column(t, vals, v, page_size=1000, opts=sbo.make_opts(sbo.C_LZ4, ratio=2.0))
+        cols.append(sb.Column(t, v is not None, data, metas))
+        refs.append((oracle_decode_column(t, v is not None, data, metas), t, v is not None))
+    for d, (r, t, nu) in zip(ctx.decode_columns(cols), refs):
+        assert_same(d, r, t, nu)
+
+
+def test_corrupt_binary(ctx):
+    rng = np.random.default_rng(6)
+    vals, v = strings(rng, 4096, 20)
+    for opts in (sbo.make_opts(), sbo.make_opts(force=sbo.C_DICT), sbo.make_opts(force=sbo.C_FREQ)):
+        data, metas = oracle_encode_column(sbo.BINARY, vals, page_size=2048, opts=opts)
+        bad = bytearray(data)
+        bad[0] = 77
+        res = ctx.decode_columns([sb.Column(sb.BINARY, False, bytes(bad), metas)], raise_on_page_error=False)[0]
+        assert res.page_status[0] == sb._capi.SB_OUT_OF_SPEC and res.page_status[1] == 0
+        bad = bytearray(data)
+        bad[1:5] = (0x7fffffff).to_bytes(4, "little")
+        res = ctx.decode_columns([sb.Column(sb.BINARY, False, bytes(bad), metas)], raise_on_page_error=False)[0]
+        assert res.page_status[0] != 0 and res.page_status[1] == 0
