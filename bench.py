@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -271,7 +272,7 @@ def main():
         if e2e_ms is not None:
             line["e2e"] = {"value": world * bytes_out / (e2e_max * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_max,
                            "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out}
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             sbo = oracle()
             sample_rows = min(rows, 1_000_000)
             ob, dt1 = cpu_decode_time(sbo, cols, sample_rows, 1)

@@ -55,6 +55,8 @@ def assert_same(dec, ref, type_, nullable):
     else:
         assert dec.values.dtype == ref["values"].dtype
         assert np.array_equal(dec.values.view(np.uint8), ref["values"].view(np.uint8))
+    if nullable and n == 0 and ref["validity"] is None:
+        return  # nothing was ever pushed into the oracle's bitmap
     if nullable:
         assert dec.validity is not None
         assert np.array_equal(sbo.unpack_bits(dec.validity, n), sbo.unpack_bits(ref["validity"], n))
