@@ -93,7 +93,7 @@ class Decoded:
     """One decoded Arrow array.  Host mode: numpy arrays.  Device mode: raw pointers that stay
     valid until release()."""
 
-    def __init__(self, ctx, type_, out, idx, group, n_nested=0):
+    def __init__(self, ctx, type_, out, idx, group, n_nested=0, copy=True):
         self.type = type_
         self.length = int(out.length)
         self.mem = out.mem
@@ -110,7 +110,11 @@ class Decoded:
                                 "validity_ptr": out.nested_validity[d], "offsets": None, "validity": None})
         if out.mem == MEM_HOST:
             def grab(p, n):
-                return np.frombuffer(C.string_at(p, n), dtype=np.uint8).copy() if p and n else (np.zeros(0, np.uint8) if p or n == 0 else None)
+                # zero-copy view of the context's pinned host buffer; valid until release()
+                if p and n:
+                    a = np.ctypeslib.as_array((C.c_uint8 * int(n)).from_address(int(p)))
+                    return a if not copy else a.copy()
+                return np.zeros(0, np.uint8) if p or n == 0 else None
             v = grab(out.values, self.values_bytes)
             if type_ in NP_OF and v is not None:
                 v = v.view(NP_OF[type_])
@@ -124,6 +128,10 @@ class Decoded:
                     nd["offsets"] = grab(nd["offsets_ptr"], (nd["len"] + 1) * 8).view(np.int64)
                 if nd["validity_ptr"]:
                     nd["validity"] = grab(nd["validity_ptr"], (nd["len"] + 7) // 8)
+
+    def release(self):
+        """give the buffers of this call (all columns decoded together) back to the context."""
+        self._group.release()
 
     def device_view(self, which="values"):
         ptr, n = {"values": (self.values_ptr, self.values_bytes), "offsets": (self.offsets_ptr, self.offsets_bytes),
@@ -202,8 +210,10 @@ class Context:
             ins[i].n_pages = len(col.metas)
         return ins, keep
 
-    def decode_columns(self, columns, out="host", raise_on_page_error=True, per_page=False):
-        """batch_read_array for many leaf columns at once: one concatenated array per column."""
+    def decode_columns(self, columns, out="host", raise_on_page_error=True, per_page=False, copy=True):
+        """batch_read_array for many leaf columns at once: one concatenated array per column.
+        out="host", copy=False returns numpy views of the context's pinned buffers (no extra
+        host copy); they stay valid until the returned arrays' group is released."""
         n = len(columns)
         ins, keep = self._marshal(columns)
         outs = (_capi.ColumnOut * n)()
@@ -214,8 +224,8 @@ class Context:
             _lib.sb_release_columns(self._h, outs, n)
             raise StrawboatError(rc, msg)
         group = _OutGroup(self, outs, n, [len(c.metas) for c in columns])
-        res = [Decoded(self, columns[i].type, outs[i], i, group, columns[i].leaf.n_nested) for i in range(n)]
-        if out == "host":
+        res = [Decoded(self, columns[i].type, outs[i], i, group, columns[i].leaf.n_nested, copy) for i in range(n)]
+        if out == "host" and copy:
             group.release()
         return res
 
@@ -226,3 +236,140 @@ class Context:
     def decode_pages(self, pages, out="host", raise_on_page_error=True):
         """column_iter_to_arrays(...).next(): one array per page; `pages` are one-page Columns."""
         return self.decode_columns(pages, out=out, raise_on_page_error=raise_on_page_error, per_page=True)
+
+
+# ---- encode ------------------------------------------------------------------------------
+def write_options(default_compression=C_NONE, default_compress_ratio=None, max_page_size=None, forbidden=(), force_codec=-1, seed=0):
+    """WriteOptions (src/write/common.rs:37-45) + the explicit sampler seed / force-codec knobs."""
+    o = _capi.WriteOptions()
+    o.default_compression = default_compression
+    o.default_compress_ratio = -1.0 if default_compress_ratio is None else float(default_compress_ratio)
+    o.max_page_size = 0 if not max_page_size else int(max_page_size)
+    m = 0
+    for c in forbidden:
+        m |= 1 << c
+    o.forbidden_mask = m
+    o.force_codec = force_codec
+    o.seed = seed
+    return o
+
+
+class LeafArray:
+    """One flat leaf array (what to_leaves yields, src/write/common.rs:68).
+
+    values   : numpy array (primitives), bool ndarray (BOOL), (offsets, data) for BINARY / LARGE_BINARY;
+               torch CUDA tensors are accepted for device-resident input
+    validity : bool ndarray, one entry per row (or a packed LSB-first uint8 bitmap when
+               `packed_validity`; device tensors are always packed), or None
+    """
+
+    def __init__(self, type_, values, validity=None, nullable=None, length=None, packed_validity=False):
+        self.type = type_
+        self.nullable = (validity is not None) if nullable is None else bool(nullable)
+        self._keep = []
+        self.offsets_ptr = 0
+        self.values_bytes = 0
+        self.mem = MEM_HOST
+
+        def host(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            self._keep.append(a)
+            return (a.ctypes.data if a.size else 0), a.nbytes
+
+        def dev(t):
+            self._keep.append(t)
+            self.mem = MEM_DEVICE
+            return t.data_ptr(), t.numel() * t.element_size()
+
+        is_dev = lambda x: hasattr(x, "data_ptr")  # noqa: E731
+        if type_ == NULL:
+            self.length = int(values if length is None else length)
+            self.values_ptr = 0
+        elif type_ == BOOL:
+            if is_dev(values):
+                assert length is not None, "device BOOL input is a packed bitmap: pass length"
+                self.values_ptr, self.values_bytes = dev(values)
+                self.length = int(length)
+            else:
+                self.length = len(values)
+                self.values_ptr, self.values_bytes = host(np.packbits(np.asarray(values, dtype=bool), bitorder="little"), np.uint8)
+        elif type_ in (BINARY, LARGE_BINARY):
+            offsets, data = values[0], values[1]
+            if is_dev(offsets):
+                self.offsets_ptr, _ = dev(offsets)
+                self.values_ptr, self.values_bytes = dev(data)
+                self.length = offsets.numel() - 1
+            else:
+                self.offsets_ptr, _ = host(offsets, np.int64 if type_ == LARGE_BINARY else np.int32)
+                self.values_ptr, self.values_bytes = host(data, np.uint8)
+                self.length = len(offsets) - 1
+        else:
+            if is_dev(values):
+                self.values_ptr, self.values_bytes = dev(values)
+                self.length = values.numel()
+            else:
+                self.values_ptr, self.values_bytes = host(values, NP_OF[type_])
+                self.length = len(values)
+        self.validity_ptr = 0
+        if validity is not None:
+            if is_dev(validity):
+                self.validity_ptr, _ = dev(validity)  # packed bitmap
+            else:
+                v = np.asarray(validity)
+                if not packed_validity:
+                    assert len(v) == self.length, "validity must have one entry per row"
+                    v = np.packbits(v.astype(bool), bitorder="little")
+                self.validity_ptr, _ = host(v, np.uint8)
+
+
+class Encoded:
+    """Encoded pages of one leaf column: `data` = the column body (pages back to back),
+    `metas` = [(length, num_values)] for the footer (PageMeta, src/lib.rs:71-80)."""
+
+    def __init__(self, out, copy=True):
+        self.metas = [(int(out.metas[i].length), int(out.metas[i].num_values)) for i in range(out.n_pages)]
+        self.nbytes = int(out.nbytes)
+        self.ptr = out.bytes
+        self.mem = out.mem
+        self.data = None
+        if out.mem == MEM_HOST:
+            self.data = C.string_at(out.bytes, self.nbytes) if self.nbytes else b""
+
+
+def _encode_columns(self, arrays, options=None, out="host"):
+    """NativeWriter::encode_chunk page loop for flat leaves, on the GPU."""
+    options = options or write_options()
+    n = len(arrays)
+    ins = (_capi.LeafArray * n)()
+    for i, a in enumerate(arrays):
+        ins[i].leaf = make_leaf(a.type, a.nullable)
+        ins[i].length = a.length
+        ins[i].values = a.values_ptr
+        ins[i].values_bytes = a.values_bytes
+        ins[i].offsets = a.offsets_ptr
+        ins[i].validity = a.validity_ptr
+        ins[i].mem = a.mem
+    outs = (_capi.EncodedColumn * n)()
+    rc = _lib.sb_encode_columns(self._h, ins, n, C.byref(options), MEM_HOST if out == "host" else MEM_DEVICE, outs)
+    if rc != _capi.SB_OK:
+        msg = _lib.sb_last_error(self._h).decode()
+        _lib.sb_release_encoded(self._h, outs, n)
+        raise StrawboatError(rc, msg)
+    res = [Encoded(outs[i]) for i in range(n)]
+    if out == "host":
+        _lib.sb_release_encoded(self._h, outs, n)
+    else:
+        for r in res:
+            r._outs, r._n, r._ctx = outs, n, self
+    return res
+
+
+def _release_encoded(self, encoded):
+    if encoded and getattr(encoded[0], "_outs", None) is not None:
+        _lib.sb_release_encoded(self._h, encoded[0]._outs, encoded[0]._n)
+        for r in encoded:
+            r._outs = None
+
+
+Context.encode_columns = _encode_columns
+Context.release_encoded = _release_encoded

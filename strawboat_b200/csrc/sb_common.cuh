@@ -288,4 +288,36 @@ struct Dctx {
   __device__ __forceinline__ void flag(int code) { atomicCAS(err, 0, code); }
 };
 
+// ------------------------------------------------------------------------------------
+// byte copy, arbitrary source alignment -> destination (basic.rs:67-70 `None`)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_bytes(uint8_t *dst, const uint8_t *src, uint64_t nbytes) {
+  const uint32_t tid = threadIdx.x;
+  uint64_t head = min(nbytes, uint64_t((16 - (uintptr_t(dst) & 15)) & 15));
+  for (uint64_t i = tid; i < head; i += SB_NT) dst[i] = src[i];
+  dst += head;
+  src += head;
+  nbytes -= head;
+  uint64_t nvec = nbytes >> 4;
+  if ((uintptr_t(src) & 15) == 0) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    uint64_t v = tid;
+    for (; v + 3 * SB_NT < nvec; v += 4 * SB_NT) { // 4 independent 16-byte loads in flight
+      uint4 a = s[v], b = s[v + SB_NT], c = s[v + 2 * SB_NT], e = s[v + 3 * SB_NT];
+      d[v] = a, d[v + SB_NT] = b, d[v + 2 * SB_NT] = c, d[v + 3 * SB_NT] = e;
+    }
+    for (; v < nvec; v += SB_NT) d[v] = s[v];
+  } else {
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    uint64_t v = tid;
+    for (; v + SB_NT < nvec; v += 2 * SB_NT) {
+      uint4 a = ld_u128u(src + (v << 4)), b = ld_u128u(src + ((v + SB_NT) << 4));
+      d[v] = a, d[v + SB_NT] = b;
+    }
+    for (; v < nvec; v += SB_NT) d[v] = ld_u128u(src + (v << 4));
+  }
+  for (uint64_t i = (nvec << 4) + tid; i < nbytes; i += SB_NT) dst[i] = src[i];
+}
+
 } // namespace sb

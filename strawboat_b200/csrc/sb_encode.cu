@@ -1,0 +1,425 @@
+// sb_encode.cu -- encode half of libstrawboat_b200.so: sb_encode_columns replaces the page loop of
+// NativeWriter::encode_chunk for flat leaves (src/write/common.rs:71-115 -> write::write,
+// src/write/serialize.rs:36-132 -> compress_integer / compress_double / compress_binary /
+// compress_boolean).
+//
+//   host : split every leaf into pages of max_page_size rows, give each page a slab sized by
+//          its worst-case encoding
+//   E*   : sb_encode_kernel   persistent grid, one CTA per page: [validity section] + stats +
+//          chooser + codec into the slab, page length out
+//   host : exclusive scan of the page lengths per column (PageMeta.length, column body size)
+//   E12  : sb_gather_kernel   slabs -> contiguous column bodies (what the file holds between
+//          ColumnMeta.offset and the next column)
+// No CPU fallback: without a CUDA device every entry point returns SB_CUDA.
+#include <cstdio>
+#include <new>
+
+#include "sb_common.cuh"
+#include "sb_encode.cuh"
+#include "sb_host.h"
+
+namespace sb {
+
+struct EncCol {
+  int32_t type, nullable, W, tclass;
+  const uint8_t *values, *offsets, *validity;
+  uint64_t length, values_bytes;
+};
+struct EncPage {
+  uint64_t row0, slab_off, dst_off;
+  uint32_t col, n, ordinal, pad;
+};
+
+constexpr uint32_t kEncSmem = 48 * 1024;
+
+__global__ void __launch_bounds__(SB_NT)
+    sb_encode_kernel(const EncPage *__restrict__ pages, const EncCol *__restrict__ cols, uint32_t n_pages, uint32_t *counter,
+                     uint8_t *slab, uint8_t *scratch, uint64_t scratch_per_cta, uint32_t *page_len, int32_t *status, EOpts base,
+                     uint32_t *codec_hist) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ int s_err;
+  __shared__ uint32_t s_ws[SB_NWARP + 1];
+  __shared__ int s_bcast[4];
+  __shared__ uint32_t s_item;
+  const uint32_t tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      s_item = atomicAdd(counter, 1u);
+      s_err = 0;
+    }
+    __syncthreads();
+    const uint32_t it = s_item;
+    if (it >= n_pages) break;
+    const EncPage pg = pages[it];
+    const EncCol &col = cols[pg.col];
+    Dctx cx;
+    cx.err = &s_err;
+    cx.ws = s_ws;
+    cx.bcast = s_bcast;
+    cx.ar.s_cur = dsm;
+    cx.ar.s_end = dsm + kEncSmem;
+    cx.ar.g_cur = scratch + uint64_t(blockIdx.x) * scratch_per_cta;
+    cx.ar.g_end = cx.ar.g_cur + scratch_per_cta;
+    EOpts o = base;
+    o.seed = base.seed + pg.ordinal; // page p of a column samples with seed + p
+    uint8_t *out = slab + pg.slab_off;
+    const uint32_t n = pg.n;
+    uint32_t pos = 0;
+    if (col.type != SB_NULL) { // Null-typed column: empty page (serialize.rs:63)
+      const Bits valid{col.validity, pg.row0};
+      if (col.nullable) pos += enc_validity(valid, n, out);
+      uint32_t used;
+      if (col.type == SB_BOOL) {
+        used = enc_boolean(cx, Bits{col.values, pg.row0}, valid, n, o, out + pos);
+      } else if (col.type == SB_BINARY || col.type == SB_LARGE_BINARY) {
+        used = enc_binary(cx, BinView{col.values, col.offsets + pg.row0 * uint64_t(col.W), col.W}, valid, n, col.values_bytes, o,
+                          out + pos);
+      } else {
+        used = enc_fixed<0>(cx, Vals{col.values + pg.row0 * uint64_t(col.W), col.W}, col.tclass, valid, n, o, out + pos);
+      }
+      if (used == kEncFail) {
+        if (!s_err) cx.flag(SB_EXTERNAL);
+        used = 0;
+      } else if (tid == 0) {
+        atomicAdd(codec_hist + (out[pos] & 31), 1u);
+      }
+      pos += used;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      page_len[it] = s_err ? 0u : pos;
+      if (s_err) status[it] = s_err;
+    }
+  }
+}
+
+// slabs -> contiguous column bodies
+__global__ void __launch_bounds__(SB_NT)
+    sb_gather_kernel(const EncPage *__restrict__ pages, uint32_t n_pages, const uint32_t *__restrict__ page_len,
+                     const uint8_t *__restrict__ slab, uint8_t *const *__restrict__ col_dst, uint32_t *counter) {
+  __shared__ uint32_t s_item;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(counter, 1u);
+    __syncthreads();
+    const uint32_t it = s_item;
+    if (it >= n_pages) break;
+    const EncPage pg = pages[it];
+    copy_bytes(col_dst[pg.col] + pg.dst_off, slab + pg.slab_off, page_len[it]);
+  }
+}
+
+// offsets[row0 of every page] (and the final offset) of binary columns, for slab sizing
+__global__ void sb_page_offsets_kernel(const EncPage *__restrict__ pages, const EncCol *__restrict__ cols, uint32_t n_pages,
+                                       int64_t *out /* 2 per page: first, last */) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pages) return;
+  const EncPage pg = pages[i];
+  const EncCol &c = cols[pg.col];
+  if (c.type != SB_BINARY && c.type != SB_LARGE_BINARY) {
+    out[2 * i] = out[2 * i + 1] = 0;
+    return;
+  }
+  if (c.W == 4) {
+    const int32_t *o = reinterpret_cast<const int32_t *>(c.offsets);
+    out[2 * i] = o[pg.row0];
+    out[2 * i + 1] = o[pg.row0 + pg.n];
+  } else {
+    const int64_t *o = reinterpret_cast<const int64_t *>(c.offsets);
+    out[2 * i] = o[pg.row0];
+    out[2 * i + 1] = o[pg.row0 + pg.n];
+  }
+}
+
+} // namespace sb
+
+using namespace sb;
+
+namespace {
+struct EncOwner {
+  void *dev = nullptr;
+  PinnedBlock pinned{nullptr, 0};
+  void *metas = nullptr;
+};
+} // namespace
+
+extern "C" {
+
+void sb_release_encoded(sb_ctx *ctx, sb_encoded_column *outs, uint64_t n) {
+  if (!ctx || !outs) return;
+  cudaSetDevice(ctx->device);
+  for (uint64_t i = 0; i < n; ++i) {
+    EncOwner *o = static_cast<EncOwner *>(outs[i]._owner);
+    if (!o) continue;
+    if (o->dev) cudaFreeAsync(o->dev, ctx->stream);
+    if (o->pinned.p) pinned_put(ctx, o->pinned);
+    std::free(o->metas);
+    delete o;
+    std::memset(&outs[i], 0, sizeof(outs[i]));
+  }
+}
+
+int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_cols, const sb_write_options *opts, int32_t out_mem,
+                          sb_encoded_column *outs) {
+  if (!ctx) return SB_CUDA;
+  if (!cols || !outs || !opts || (out_mem != SB_MEM_HOST && out_mem != SB_MEM_DEVICE)) return fail(ctx, SB_INVALID_ARG, "bad arguments");
+  if (opts->default_compression == SB_C_ZSTD || opts->default_compression == SB_C_SNAPPY)
+    return fail(ctx, SB_NYI, "zstd / snappy page writers are not implemented (SURVEY 8 f3)");
+  if (opts->default_compression != SB_C_NONE && opts->default_compression != SB_C_LZ4)
+    return fail(ctx, SB_OUT_OF_SPEC, "default_compression must be a common codec (None / LZ4 / Zstd / Snappy)");
+  SB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  std::memset(outs, 0, sizeof(sb_encoded_column) * n_cols);
+  ctx->stats = sb_stats{};
+
+  // ---- page split (NativeWriter::encode_chunk, write/common.rs:54-58,79-86)
+  std::vector<EncCol> h_cols(n_cols);
+  std::vector<EncPage> h_pages;
+  std::vector<uint64_t> col_first_page(n_cols + 1, 0);
+  std::vector<void *> d_inputs;
+  auto free_inputs = [&]() {
+    for (void *d : d_inputs) cudaFreeAsync(d, st);
+    d_inputs.clear();
+  };
+  auto upload = [&](const void *src, uint64_t bytes, int mem, const uint8_t **dst) -> int {
+    *dst = static_cast<const uint8_t *>(src);
+    if (!src || mem == SB_MEM_DEVICE || bytes == 0) return SB_OK;
+    void *d = nullptr;
+    SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, align_up(bytes + 32, 256), st));
+    d_inputs.push_back(d);
+    SB_CUDA_CHECK(ctx, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
+    *dst = static_cast<const uint8_t *>(d);
+    return SB_OK;
+  };
+  uint64_t bytes_in = 0, max_rows = 0;
+  bool any_binary = false;
+  for (uint64_t c = 0; c < n_cols; ++c) {
+    const sb_leaf_array &a = cols[c];
+    if (a.leaf.type < SB_NULL || a.leaf.type > SB_LARGE_BINARY) return fail(ctx, SB_NYI, "unsupported physical type");
+    if (a.leaf.n_nested > 1) return fail(ctx, SB_NYI, "nested leaves: encode the rep/def levels on the host (not implemented)");
+    EncCol &ec = h_cols[c];
+    std::memset(&ec, 0, sizeof(ec));
+    ec.type = a.leaf.type;
+    ec.nullable = a.leaf.nullable != 0;
+    ec.W = type_width(a.leaf.type);
+    ec.tclass = (a.leaf.type == SB_F32 || a.leaf.type == SB_F64) ? TC_FLOAT : (a.leaf.type >= SB_I8 && a.leaf.type <= SB_I64) ? TC_SINT : TC_UINT;
+    ec.length = a.length;
+    ec.values_bytes = a.values_bytes;
+    const bool binary = a.leaf.type == SB_BINARY || a.leaf.type == SB_LARGE_BINARY;
+    any_binary |= binary;
+    if (a.length && a.leaf.type != SB_NULL && !a.values && !(binary && a.values_bytes == 0)) return fail(ctx, SB_INVALID_ARG, "values is NULL");
+    if (binary && !a.offsets) return fail(ctx, SB_INVALID_ARG, "offsets is NULL");
+    uint64_t vbytes = a.leaf.type == SB_BOOL ? (a.length + 7) / 8 : binary ? a.values_bytes : a.length * uint64_t(ec.W);
+    int rc;
+    if ((rc = upload(a.values, vbytes, a.mem, &ec.values)) || (rc = upload(binary ? a.offsets : nullptr, (a.length + 1) * uint64_t(ec.W), a.mem, &ec.offsets)) ||
+        (rc = upload(a.validity, (a.length + 7) / 8, a.mem, &ec.validity))) {
+      free_inputs();
+      return rc;
+    }
+    if (fixed_type(a.leaf.type) && (uintptr_t(ec.values) % uintptr_t(ec.W)) != 0) {
+      free_inputs();
+      return fail(ctx, SB_INVALID_ARG, "values must be aligned to the element width");
+    }
+    bytes_in += vbytes + (binary ? (a.length + 1) * uint64_t(ec.W) : 0) + (a.validity ? (a.length + 7) / 8 : 0);
+    col_first_page[c] = h_pages.size();
+    const uint64_t page_rows = opts->max_page_size ? std::min<uint64_t>(opts->max_page_size, a.length) : a.length;
+    for (uint64_t r = 0, p = 0; r < a.length; r += page_rows, ++p) {
+      EncPage pg{};
+      pg.row0 = r;
+      pg.n = uint32_t(std::min<uint64_t>(page_rows, a.length - r));
+      pg.col = uint32_t(c);
+      pg.ordinal = uint32_t(p);
+      if (page_rows > 0xfffffff0ull) {
+        free_inputs();
+        return fail(ctx, SB_OUT_OF_SPEC, "page larger than 2^32 rows (u32 size fields)");
+      }
+      h_pages.push_back(pg);
+      max_rows = std::max<uint64_t>(max_rows, pg.n);
+    }
+  }
+  col_first_page[n_cols] = h_pages.size();
+  const uint64_t n_pages = h_pages.size();
+
+  // device tables: [EncCol][EncPage][page_len][status][counters 2 + hist 32][col_dst ptrs][page offsets 2 x i64]
+  size_t off_cols = 0;
+  size_t off_pages = align_up(off_cols + sizeof(EncCol) * n_cols, 16);
+  size_t off_len = align_up(off_pages + sizeof(EncPage) * n_pages, 16);
+  size_t off_status = align_up(off_len + 4 * n_pages, 16);
+  size_t off_ctr = align_up(off_status + 4 * n_pages, 16);
+  size_t off_dst = align_up(off_ctr + 4 * 36, 16);
+  size_t off_po = align_up(off_dst + 8 * n_cols, 16);
+  size_t tbytes = align_up(off_po + 16 * n_pages, 16);
+  int rc;
+  if ((rc = host_tables_reserve(ctx, tbytes)) || (rc = dev_reserve(ctx, ctx->d_tables, tbytes))) {
+    free_inputs();
+    return rc;
+  }
+  uint8_t *hT = static_cast<uint8_t *>(ctx->h_tables), *dT = static_cast<uint8_t *>(ctx->d_tables.p);
+#define SB_ETRY(call)                                                                 \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      free_inputs();                                                                  \
+      sb_release_encoded(ctx, outs, n_cols);                                          \
+      return fail(ctx, SB_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    }                                                                                 \
+  } while (0)
+  std::memcpy(hT + off_cols, h_cols.data(), sizeof(EncCol) * n_cols);
+  EncPage *hp = reinterpret_cast<EncPage *>(hT + off_pages);
+  if (n_pages) std::memcpy(hp, h_pages.data(), sizeof(EncPage) * n_pages);
+  const EncCol *d_cols = reinterpret_cast<const EncCol *>(dT + off_cols);
+  const EncPage *d_pages = reinterpret_cast<const EncPage *>(dT + off_pages);
+
+  // ---- slab sizing (worst-case page encodings)
+  std::vector<int64_t> page_bytes(n_pages, 0);
+  if (any_binary && n_pages) {
+    SB_ETRY(cudaMemcpyAsync(dT, hT, off_len, cudaMemcpyHostToDevice, st));
+    sb_page_offsets_kernel<<<uint32_t((n_pages + 255) / 256), 256, 0, st>>>(d_pages, d_cols, uint32_t(n_pages), reinterpret_cast<int64_t *>(dT + off_po));
+    SB_ETRY(cudaMemcpyAsync(hT + off_po, dT + off_po, 16 * n_pages, cudaMemcpyDeviceToHost, st));
+    SB_ETRY(cudaStreamSynchronize(st));
+    const int64_t *po = reinterpret_cast<const int64_t *>(hT + off_po);
+    for (uint64_t i = 0; i < n_pages; ++i) {
+      page_bytes[i] = po[2 * i + 1] - po[2 * i];
+      if (page_bytes[i] < 0 || page_bytes[i] > 0xfffffff0ll) {
+        free_inputs();
+        return fail(ctx, SB_OUT_OF_SPEC, "binary offsets are not monotone, or a page holds more than 4 GiB of values");
+      }
+    }
+  }
+  uint64_t slab_total = 0;
+  for (uint64_t i = 0; i < n_pages; ++i) {
+    EncPage &pg = hp[i];
+    const EncCol &ec = h_cols[pg.col];
+    const uint64_t n = pg.n;
+    uint64_t cap = 64 + (ec.nullable ? 16 + n / 8 : 0);
+    if (ec.type == SB_BOOL) cap += 5 * n + 64;
+    else if (ec.type == SB_BINARY || ec.type == SB_LARGE_BINARY) cap += 2 * uint64_t(page_bytes[i]) + 25 * n + 9000 * (n / 65536 + 1) + 2048;
+    else if (ec.type != SB_NULL) cap += n * uint64_t(ec.W + 13) + 9000 * (n / 65536 + 1) + 2048;
+    if (cap > 0xffffffffull) {
+      free_inputs();
+      return fail(ctx, SB_OUT_OF_SPEC, "page larger than 4 GiB (u32 size fields)");
+    }
+    pg.slab_off = slab_total;
+    slab_total += align_up(cap, 16);
+  }
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  int occ = 1;
+  SB_ETRY(cudaFuncSetAttribute(sb_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kEncSmem)));
+  SB_ETRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_encode_kernel, SB_NT, kEncSmem));
+  occ = std::max(1, occ);
+  const uint64_t scratch_per_cta = align_up(176 * max_rows + 128 * 1024, 256);
+  uint64_t grid = std::min<uint64_t>(std::max<uint64_t>(n_pages, 1), uint64_t(ctx->sm_count) * occ);
+  grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (uint64_t(8) << 30) / scratch_per_cta));
+  void *d_slab = nullptr;
+  if (n_pages) {
+    if (slab_total + scratch_per_cta * grid > free_b + ctx->d_scratch.cap) {
+      free_inputs();
+      return fail(ctx, SB_NYI, "encode batch does not fit in device memory: split the call into fewer columns");
+    }
+    SB_ETRY(cudaMallocAsync(&d_slab, slab_total + 64, st));
+    d_inputs.push_back(d_slab);
+    if ((rc = dev_reserve(ctx, ctx->d_scratch, scratch_per_cta * grid))) {
+      free_inputs();
+      return rc;
+    }
+    SB_ETRY(cudaMemcpyAsync(dT, hT, off_len, cudaMemcpyHostToDevice, st));
+    SB_ETRY(cudaMemsetAsync(dT + off_len, 0, off_dst - off_len, st));
+    EOpts eo;
+    eo.def_codec = opts->default_compression;
+    eo.ratio = opts->default_compress_ratio;
+    eo.forbidden = opts->forbidden_mask;
+    eo.force = opts->force_codec;
+    eo.seed = opts->seed;
+    uint32_t *d_ctr = reinterpret_cast<uint32_t *>(dT + off_ctr);
+    SB_ETRY(cudaEventRecord(ctx->ev0, st));
+    sb_encode_kernel<<<uint32_t(grid), SB_NT, kEncSmem, st>>>(d_pages, d_cols, uint32_t(n_pages), d_ctr, static_cast<uint8_t *>(d_slab),
+                                                             static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta,
+                                                             reinterpret_cast<uint32_t *>(dT + off_len), reinterpret_cast<int32_t *>(dT + off_status), eo,
+                                                             d_ctr + 4);
+    SB_ETRY(cudaGetLastError());
+    SB_ETRY(cudaEventRecord(ctx->ev1, st));
+    ctx->stats.kernel_launches += 1;
+    SB_ETRY(cudaMemcpyAsync(hT + off_len, dT + off_len, off_dst - off_len, cudaMemcpyDeviceToHost, st));
+    SB_ETRY(cudaStreamSynchronize(st));
+  }
+
+  // ---- PageMeta + column bodies
+  const uint32_t *h_len = reinterpret_cast<const uint32_t *>(hT + off_len);
+  const int32_t *h_status = reinterpret_cast<const int32_t *>(hT + off_status);
+  void **h_dst = reinterpret_cast<void **>(hT + off_dst);
+  int32_t first_err = SB_OK;
+  uint64_t bytes_out = 0;
+  for (uint64_t c = 0; c < n_cols; ++c) {
+    EncOwner *ow = new EncOwner();
+    outs[c]._owner = ow;
+    outs[c].mem = out_mem;
+    const uint64_t p0 = col_first_page[c], p1 = col_first_page[c + 1];
+    outs[c].n_pages = p1 - p0;
+    sb_page_meta *metas = static_cast<sb_page_meta *>(std::malloc(sizeof(sb_page_meta) * std::max<uint64_t>(1, p1 - p0)));
+    ow->metas = metas;
+    outs[c].metas = metas;
+    uint64_t pos = 0;
+    for (uint64_t p = p0; p < p1; ++p) {
+      if (h_status[p] != SB_OK && first_err == SB_OK) {
+        first_err = h_status[p];
+        ctx->err = "page " + std::to_string(p - p0) + " of column " + std::to_string(c) + " failed to encode with status " + std::to_string(h_status[p]);
+      }
+      metas[p - p0].length = h_len[p];
+      metas[p - p0].num_values = hp[p].n; // rows for flat leaves (common.rs:103)
+      hp[p].dst_off = pos;
+      pos += h_len[p];
+    }
+    outs[c].nbytes = pos;
+    bytes_out += pos;
+    h_dst[c] = nullptr;
+    if (pos) {
+      SB_ETRY(cudaMallocAsync(&ow->dev, pos + 16, st));
+      h_dst[c] = ow->dev;
+    }
+  }
+  if (n_pages) {
+    SB_ETRY(cudaMemcpyAsync(dT + off_pages, hT + off_pages, sizeof(EncPage) * n_pages, cudaMemcpyHostToDevice, st));
+    SB_ETRY(cudaMemcpyAsync(dT + off_dst, hT + off_dst, 8 * n_cols, cudaMemcpyHostToDevice, st));
+    uint32_t *d_ctr = reinterpret_cast<uint32_t *>(dT + off_ctr);
+    uint32_t ggrid = uint32_t(std::min<uint64_t>(n_pages, uint64_t(ctx->sm_count) * 8));
+    sb_gather_kernel<<<ggrid, SB_NT, 0, st>>>(d_pages, uint32_t(n_pages), reinterpret_cast<const uint32_t *>(dT + off_len),
+                                              static_cast<const uint8_t *>(d_slab), reinterpret_cast<uint8_t *const *>(dT + off_dst), d_ctr + 1);
+    SB_ETRY(cudaGetLastError());
+    ctx->stats.kernel_launches += 1;
+  }
+  for (uint64_t c = 0; c < n_cols; ++c) {
+    EncOwner *ow = static_cast<EncOwner *>(outs[c]._owner);
+    if (out_mem == SB_MEM_DEVICE) {
+      outs[c].bytes = static_cast<uint8_t *>(ow->dev);
+    } else if (outs[c].nbytes) {
+      if ((rc = pinned_get(ctx, outs[c].nbytes, &ow->pinned))) {
+        free_inputs();
+        sb_release_encoded(ctx, outs, n_cols);
+        return rc;
+      }
+      SB_ETRY(cudaMemcpyAsync(ow->pinned.p, ow->dev, outs[c].nbytes, cudaMemcpyDeviceToHost, st));
+      outs[c].bytes = static_cast<uint8_t *>(ow->pinned.p);
+    }
+  }
+  free_inputs();
+  SB_ETRY(cudaStreamSynchronize(st));
+  if (out_mem == SB_MEM_HOST)
+    for (uint64_t c = 0; c < n_cols; ++c) {
+      EncOwner *ow = static_cast<EncOwner *>(outs[c]._owner);
+      if (ow->dev) cudaFreeAsync(ow->dev, st);
+      ow->dev = nullptr;
+    }
+  if (n_pages) cudaEventElapsedTime(&ctx->stats.device_ms, ctx->ev0, ctx->ev1);
+  const uint32_t *h_ctr = reinterpret_cast<const uint32_t *>(hT + off_ctr);
+  if (n_pages)
+    for (int i = 0; i < 32; ++i) ctx->stats.codec_pages[i] = h_ctr[4 + i];
+  ctx->stats.pages = n_pages;
+  ctx->stats.bytes_in = bytes_in;
+  ctx->stats.bytes_out = bytes_out;
+  return first_err;
+#undef SB_ETRY
+}
+
+} // extern "C"

@@ -17,8 +17,9 @@
 
 namespace sb {
 
-constexpr uint32_t SB_LZ4_RING = 16384;  // per-warp output ring bytes
-constexpr uint32_t SB_LZ4_IN = 4096;     // per-warp input ring bytes (two halves, cp.async prefetched)
+constexpr uint32_t SB_LZ4_RING = 8192;   // per-warp output ring bytes
+constexpr uint32_t SB_LZ4_IN = 2048;     // per-warp input ring bytes (two halves, cp.async prefetched)
+constexpr uint32_t SB_LZ4_CHUNK = SB_LZ4_IN / 2;
 constexpr uint32_t SB_LZ4_FLUSH = 2048;  // flush granularity
 constexpr uint32_t SB_LZ4_PIECE = 1024;  // long literal / match runs are moved in pieces
 
@@ -170,14 +171,14 @@ struct Lz4Stream {
 
   __device__ __forceinline__ void issue_chunk() { // request the next 2 KiB (or the tail)
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t end = min(total, issued + 2048u);
+    uint32_t end = min(total, issued + SB_LZ4_CHUNK);
     for (uint32_t o = issued + lane * 16; o < end; o += 512) cp_async16(in + (o & (SB_LZ4_IN - 1)), gal + o);
     cp_async_commit();
     issued = end;
   }
   // make stream bytes [0, q_end) readable; keeps one chunk of prefetch in flight
   __device__ __forceinline__ void ensure(uint32_t q, uint32_t q_end) {
-    if (issued < total && q + 2048 >= issued) { // the half before `q`'s half is free again
+    if (issued < total && q + SB_LZ4_CHUNK >= issued) { // the half before `q`'s half is free again
       __syncwarp();
       issue_chunk();
     }
@@ -190,7 +191,7 @@ struct Lz4Stream {
   __device__ __forceinline__ void in_reset(uint32_t q) { // restart streaming at stream position q
     cp_async_wait_all();
     __syncwarp();
-    issued = q & ~2047u;
+    issued = q & ~(SB_LZ4_CHUNK - 1);
     ready = issued;
     issue_chunk();
     if (issued < total) issue_chunk();
@@ -272,7 +273,7 @@ __device__ int lz4_decode_stream(const uint8_t *src, uint32_t clen, uint8_t *dst
       uint32_t q = mis + ip;
       s.ensure(q, min(s.total, q + 48));
       s.advance(op);
-      ip_lim = (s.ready >= s.total) ? 0xffffffffu : min(s.ready - 48, s.issued - 2048) - mis;
+      ip_lim = (s.ready >= s.total) ? 0xffffffffu : min(s.ready - 48, s.issued - SB_LZ4_CHUNK) - mis;
       op_lim = s.fl + SB_LZ4_FLUSH;
       tok = lds_u8(in_b + (q & IM));
       b = lds_u8(in_b + ((q + 1 + lane) & IM));
