@@ -55,7 +55,7 @@ def check(ctx, type_, values, validity=None, nullable=None, page_size=2048, defa
         else:
             for i in np.flatnonzero(vmask)[:: max(1, n // 500)]:
                 assert np.array_equal(ref["values"][ro[i]:ro[i + 1]], dat[off[i]:off[i + 1]])
-    elif type_ != sbo.NULL:
+    elif type_ != sbo.NULL and n:
         v = np.ascontiguousarray(values, dtype=sbo.NP_OF[type_])
         assert np.array_equal(ref["values"].view(np.uint8).reshape(n, -1)[vmask], v.view(np.uint8).reshape(n, -1)[vmask])
     if nullable and n:
