@@ -28,7 +28,7 @@ constexpr uint32_t kEncFail = 0xffffffffu;
 __device__ __forceinline__ bool e_forbidden(const EOpts &o, int c) { return (o.forbidden >> c) & 1u; }
 
 // the deterministic stand-in for thread_rng().gen_range (integer/mod.rs:332); shared definition
-// with the oracle's sample_draw (oracle/sb_oracle.cpp)
+// with the test oracle's sampler (same mixing constants), so chooser parity is testable
 __device__ __forceinline__ uint64_t sample_draw(uint64_t seed, uint32_t codec, uint32_t i, uint64_t range_end) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t(codec) * 16 + i + 1);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
