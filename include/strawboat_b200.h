@@ -166,6 +166,8 @@ typedef struct {
   uint64_t kernel_launches;
   float device_ms;         /* CUDA-event time of the kernels of the last call */
   uint64_t codec_pages[32]; /* pages per top-level codec id */
+  float main_kernel_ms;    /* decode: sb_decode_kernel (pass 1) alone */
+  float lz4_kernel_ms;     /* decode: sb_lz4_kernel alone (runs concurrently with the main kernel) */
 } sb_stats;
 int32_t sb_last_stats(const sb_ctx *ctx, sb_stats *out);
 

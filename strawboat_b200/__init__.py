@@ -192,6 +192,7 @@ class Context:
         self._check(_lib.sb_last_stats(self._h, C.byref(s)))
         return {"pages": s.pages, "bytes_in": s.bytes_in, "bytes_out": s.bytes_out,
                 "kernel_launches": s.kernel_launches, "device_ms": s.device_ms,
+                "main_kernel_ms": s.main_kernel_ms, "lz4_kernel_ms": s.lz4_kernel_ms,
                 "codec_pages": {i: s.codec_pages[i] for i in range(32) if s.codec_pages[i]}}
 
     # ---- decode ----------------------------------------------------------------------

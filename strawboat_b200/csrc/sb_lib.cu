@@ -64,6 +64,21 @@ __device__ __forceinline__ bool lz4_side_page(const uint8_t *p, uint32_t len, bo
   return true;
 }
 
+// side_flags: 0 = decoded by the main kernel, 1 = top-level LZ4 block -> sb_lz4_kernel,
+// 2 = "stored" LZ4 block (one literal run covering the whole output: what LZ4 emits for
+// incompressible data) -> plain copy in the main kernel.
+// Jobs are binned by compressed size: long streams from the front of `jobs`, short ones from
+// the back, so the (latency-bound) long pages start first and the short ones fill the tail.
+__device__ __forceinline__ bool lz4_stored_block(const uint8_t *s, uint32_t clen, uint32_t dlen, uint32_t *lit_start) {
+  if (dlen < 15 || clen < 2 || s[0] != 0xF0) return false;
+  uint32_t ne = (dlen - 15) / 255 + 1; // length-extension bytes: (ne-1) x 255, then the rest
+  if (ne > 2048 || uint64_t(clen) != 1ull + ne + dlen) return false;
+  bool ok = s[ne] == (dlen - 15) % 255;
+  for (uint32_t i = 1; i < ne; ++i) ok &= s[i] == 255;
+  *lit_start = 1 + ne;
+  return ok;
+}
+
 __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, uint32_t n_pages,
                                    Lz4Job *jobs, uint32_t *n_jobs, uint8_t *side_flags) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,34 +88,53 @@ __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const Col
   if (!is_fixed_type(col.type) || col.n_nested > 1) return;
   uint32_t vb, clen;
   if (!lz4_side_page(pg.src, pg.len, col.nullable != 0, &vb, &clen)) return;
-  uint32_t slot = atomicAdd(n_jobs, 1u);
+  const uint32_t dlen = pg.num_values * uint32_t(col.W);
+  uint32_t lit_start;
+  if (lz4_stored_block(pg.src + vb + 9, clen, dlen, &lit_start)) {
+    side_flags[i] = 2;
+    return;
+  }
   Lz4Job j;
   j.src = pg.src + vb + 9;
   j.dst = col.values + pg.out_elem * uint64_t(col.W);
   j.clen = clen;
-  j.dlen = pg.num_values * uint32_t(col.W);
+  j.dlen = dlen;
   j.page = i;
   j.pad = 0;
+  // n_jobs[0] = long jobs (front), n_jobs[1] = short jobs (back)
+  const bool big = clen >= 8192;
+  uint32_t slot = big ? atomicAdd(n_jobs, 1u) : n_pages - 1 - atomicAdd(n_jobs + 1, 1u);
   jobs[slot] = j;
   side_flags[i] = 1;
 }
 
-constexpr int kLz4Warps = 2;
-__global__ void __launch_bounds__(kLz4Warps * 32)
-    sb_lz4_kernel(const Lz4Job *__restrict__ jobs, const uint32_t *__restrict__ n_jobs_p, uint32_t *counter, int32_t *status) {
-  __shared__ __align__(16) uint8_t rings[kLz4Warps][SB_LZ4_RING];
-  __shared__ __align__(16) uint8_t in_rings[kLz4Warps][SB_LZ4_IN];
+__global__ void __launch_bounds__(64)
+    sb_lz4_kernel(const Lz4Job *__restrict__ jobs, const uint32_t *__restrict__ n_jobs_p, uint32_t n_pages, uint32_t *counter,
+                  int32_t *status) {
+  __shared__ Lz4PairShared sh;
+  __shared__ uint32_t s_job;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n_jobs = *n_jobs_p;
+  const uint32_t n_big = n_jobs_p[0], n_small = n_jobs_p[1];
   for (;;) {
-    uint32_t j = 0;
-    if (lane == 0) j = atomicAdd(counter, 1u);
-    j = __shfl_sync(0xffffffffu, j, 0);
-    if (j >= n_jobs) break;
-    const Lz4Job job = jobs[j];
-    int rc = lz4_decode_stream(job.src, job.clen, job.dst, job.dlen, in_rings[warp], rings[warp]);
-    if (rc && lane == 0) atomicCAS(status + job.page, 0, rc);
-    __syncwarp();
+    if (threadIdx.x == 0) {
+      s_job = atomicAdd(counter, 1u);
+      sh.produced = 0;
+      sh.consumed = 0;
+      sh.flushed = 0;
+    }
+    __syncthreads();
+    const uint32_t j = s_job;
+    if (j >= n_big + n_small) break;
+    const Lz4Job job = jobs[j < n_big ? j : n_pages - 1 - (j - n_big)];
+    if (job.clen == 0) {
+      if (job.dlen != 0 && threadIdx.x == 0) atomicCAS(status + job.page, 0, int(SB_EXTERNAL));
+    } else if (warp == 0) {
+      int rc = lz4_pair_produce(job.src, job.clen, job.dlen, &sh);
+      if (rc && lane == 0) atomicCAS(status + job.page, 0, rc);
+    } else {
+      lz4_pair_consume(job.dst, &sh);
+    }
+    __syncthreads();
   }
 }
 
@@ -141,7 +175,9 @@ __global__ void __launch_bounds__(SB_NT)
     const WorkItem wi = items[it];
     const PageDesc pg = pages[wi.page];
     const ColDesc &col = cols[pg.col];
-    const bool lz4_side = pass == 1 && side_flags != nullptr && side_flags[wi.page] != 0;
+    const uint32_t side = (pass == 1 && side_flags != nullptr) ? side_flags[wi.page] : 0u;
+    const bool lz4_side = side == 1; // value block decoded by sb_lz4_kernel
+    const bool stored = side == 2;   // LZ4 block that is one literal run: plain copy here
     if (lz4_side && !col.nullable) { // value block handled by sb_lz4_kernel, nothing else in the page
       if (tid == 0 && (wi.tile == 0 || wi.tile == 0xffffffffu)) atomicAdd(codec_hist + SB_C_LZ4, 1u);
       __syncthreads();
@@ -198,6 +234,9 @@ __global__ void __launch_bounds__(SB_NT)
       if (wi.tile == 0 && tid == 0 && codec >= 0 && codec < 32) atomicAdd(codec_hist + codec, 1u);
       if (codec == SB_C_NONE && avail >= 9 && compressed <= avail - 9 && uint64_t(compressed) == uint64_t(n) * W) {
         copy_bytes(dst + uint64_t(lo) * W, p + 9 + uint64_t(lo) * W, uint64_t(hi - lo) * W);
+      } else if (stored) { // validated by sb_classify_kernel: [token 0xF0][ne length bytes][n*W literals]
+        const uint32_t lit0 = 9 + 1 + ((n * W - 15) / 255 + 1);
+        copy_bytes(dst + uint64_t(lo) * W, p + lit0 + uint64_t(lo) * W, uint64_t(hi - lo) * W);
       } else if (codec == SB_C_ONEVALUE && avail >= 9 + W) {
         switch (W) {
         case 1: dec_onevalue<1>(cx, p + 9, avail - 9, lo, hi, dst); break;
@@ -244,7 +283,10 @@ __global__ void __launch_bounds__(SB_NT)
         } else if (is_fixed_type(col.type)) {
           uint32_t used = 0;
           // top-level LZ4 blocks are decoded by sb_lz4_kernel (same predicate as sb_classify_kernel)
-          if (!lz4_side)
+          if (stored) {
+            const uint32_t dlen = n * uint32_t(col.W);
+            copy_bytes(col.values + out_elem * uint64_t(col.W), p + vb + 9 + 1 + ((dlen - 15) / 255 + 1), dlen);
+          } else if (!lz4_side)
             ok = decode_fixed<0>(cx, p + vb, avail - vb, n, col.W, col.is_float != 0,
                                  col.values + out_elem * uint64_t(col.W), &used);
         } else if (col.type == SB_BINARY) {
@@ -294,6 +336,7 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out) {
   ctx->own_stream = true;
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
+  for (cudaEvent_t *ev : {&ctx->ev_m0, &ctx->ev_m1, &ctx->ev_lz0, &ctx->ev_lz1}) cudaEventCreate(ev);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -305,6 +348,8 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out) {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   cudaFuncSetAttribute(sb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemMax));
+  cudaFuncSetAttribute(sb_lz4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(sb_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   *out = ctx;
   return SB_OK;
 }
@@ -319,7 +364,7 @@ void sb_ctx_destroy(sb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
   for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
-  for (cudaEvent_t ev : {ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->ev_join})
+  for (cudaEvent_t ev : {ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->ev_join, ctx->ev_m0, ctx->ev_m1, ctx->ev_lz0, ctx->ev_lz1})
     if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->aux);
@@ -424,7 +469,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
 
   // one pinned staging buffer, mirrored on the device:
   //   uploaded : [ColDesc * n_cols][PageDesc * P][WorkItem * I][WorkItem * plan][PageAux * plan]
-  //   zeroed   : [status * P][counters * 36][side_flags * P]      device only: [Lz4Job * P]
+  //   zeroed   : [status * P][counters * 40][side_flags * P]      device only: [Lz4Job * P]
   size_t off_cols = 0;
   size_t off_pages = align_up(off_cols + sizeof(ColDesc) * n_cols, 16);
   size_t off_items = align_up(off_pages + sizeof(PageDesc) * n_pages_total, 16);
@@ -433,7 +478,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   size_t tables_bytes = align_up(off_aux + sizeof(PageAux) * n_plan, 16);
   size_t off_status = tables_bytes;
   size_t off_counters = align_up(off_status + sizeof(int32_t) * n_pages_total, 16);
-  size_t off_flags = off_counters + 36 * 4;
+  size_t off_flags = off_counters + 40 * 4;
   size_t zero_end = align_up(off_flags + n_pages_total, 16);
   size_t off_jobs = zero_end;
   size_t dev_bytes = off_jobs + sizeof(Lz4Job) * n_pages_total;
@@ -574,7 +619,8 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   const PageDesc *d_pages = reinterpret_cast<const PageDesc *>(dT + off_pages);
   const ColDesc *d_cols = reinterpret_cast<const ColDesc *>(dT + off_cols);
   int32_t *d_status = reinterpret_cast<int32_t *>(dT + off_status);
-  // counters: [0] main queue, [1] lz4 queue, [2] n lz4 jobs, [3] plan queue, [4..35] pages per top-level codec
+  // counters: [0] main queue, [1] lz4 queue, [2] long lz4 jobs, [3] short lz4 jobs, [4] plan queue,
+  //           [5..36] pages per top-level codec
   uint32_t *d_counters = reinterpret_cast<uint32_t *>(dT + off_counters);
   uint8_t *d_flags = dT + off_flags;
   Lz4Job *d_jobs = reinterpret_cast<Lz4Job *>(dT + off_jobs);
@@ -591,8 +637,8 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   if (n_plan) {
     uint32_t grid0 = uint32_t(std::min<uint64_t>(n_plan, uint64_t(ctx->sm_count) * occ));
     sb_decode_kernel<<<grid0, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items0), uint32_t(n_plan),
-                                                 d_counters + 3, static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta, d_status,
-                                                 stage_cap, smem, nullptr, d_aux, d_entries, d_counters + 4, 0);
+                                                 d_counters + 4, static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta, d_status,
+                                                 stage_cap, smem, nullptr, d_aux, d_entries, d_counters + 5, 0);
     SB_TRY_CUDA(cudaGetLastError());
     ctx->stats.kernel_launches += 1;
     SB_TRY_CUDA(cudaMemcpyAsync(h_aux, d_aux, sizeof(PageAux) * n_plan, cudaMemcpyDeviceToHost, st));
@@ -671,18 +717,21 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_fork, st));
       SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
       int lz4_occ = 1;
-      SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz4_occ, sb_lz4_kernel, kLz4Warps * 32, 0));
-      uint32_t lz4_grid = uint32_t(std::min<uint64_t>((n_pages_total + kLz4Warps - 1) / kLz4Warps,
-                                                      uint64_t(ctx->sm_count) * std::max(1, lz4_occ)));
-      sb_lz4_kernel<<<lz4_grid, kLz4Warps * 32, 0, ctx->aux>>>(d_jobs, d_counters + 2, d_counters + 1, d_status);
+      SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz4_occ, sb_lz4_kernel, 64, 0));
+      uint32_t lz4_grid = uint32_t(std::min<uint64_t>(n_pages_total, uint64_t(ctx->sm_count) * std::max(1, lz4_occ)));
+      SB_TRY_CUDA(cudaEventRecord(ctx->ev_lz0, ctx->aux));
+      sb_lz4_kernel<<<lz4_grid, 64, 0, ctx->aux>>>(d_jobs, d_counters + 2, uint32_t(n_pages_total), d_counters + 1, d_status);
+      SB_TRY_CUDA(cudaEventRecord(ctx->ev_lz1, ctx->aux));
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
       ctx->stats.kernel_launches += 2;
     }
+    SB_TRY_CUDA(cudaEventRecord(ctx->ev_m0, st));
     sb_decode_kernel<<<grid, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items),
                                                 uint32_t(n_items), d_counters, static_cast<uint8_t *>(ctx->d_scratch.p),
                                                 scratch_per_cta, d_status, stage_cap, smem, any_fixed ? d_flags : nullptr, d_aux,
-                                                d_entries, d_counters + 4, 1);
+                                                d_entries, d_counters + 5, 1);
     SB_TRY_CUDA(cudaGetLastError());
+    SB_TRY_CUDA(cudaEventRecord(ctx->ev_m1, st));
     if (any_fixed) SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     SB_TRY_CUDA(cudaEventRecord(ctx->ev1, st));
     ctx->stats.kernel_launches += 1;
@@ -728,13 +777,17 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       owners[c]->dev.clear();
     }
   }
-  if (n_items) cudaEventElapsedTime(&ctx->stats.device_ms, ctx->ev0, ctx->ev1);
+  if (n_items) {
+    cudaEventElapsedTime(&ctx->stats.device_ms, ctx->ev0, ctx->ev1);
+    cudaEventElapsedTime(&ctx->stats.main_kernel_ms, ctx->ev_m0, ctx->ev_m1);
+    if (any_fixed) cudaEventElapsedTime(&ctx->stats.lz4_kernel_ms, ctx->ev_lz0, ctx->ev_lz1);
+  }
 
   int32_t first_err = SB_OK;
   const int32_t *h_status = reinterpret_cast<const int32_t *>(hT + off_status);
   const uint32_t *h_counters = reinterpret_cast<const uint32_t *>(hT + off_counters);
   if (n_items)
-    for (int i = 0; i < 32; ++i) ctx->stats.codec_pages[i] = h_counters[4 + i];
+    for (int i = 0; i < 32; ++i) ctx->stats.codec_pages[i] = h_counters[5 + i];
   pi = 0;
   for (uint64_t c = 0; c < n_cols; ++c) {
     sb_column_out &o = outs[c];
