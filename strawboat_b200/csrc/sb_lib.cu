@@ -108,10 +108,10 @@ __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const Col
   side_flags[i] = 1;
 }
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, 16)
     sb_lz4_kernel(const Lz4Job *__restrict__ jobs, const uint32_t *__restrict__ n_jobs_p, uint32_t n_pages, uint32_t *counter,
                   int32_t *status) {
-  __shared__ Lz4PairShared sh;
+  __shared__ Lz4Shared sh;
   __shared__ uint32_t s_job;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_big = n_jobs_p[0], n_small = n_jobs_p[1];
@@ -119,21 +119,25 @@ __global__ void __launch_bounds__(64)
     if (threadIdx.x == 0) {
       s_job = atomicAdd(counter, 1u);
       sh.produced = 0;
+      sh.in_ready = 0;
       sh.consumed = 0;
-      sh.flushed = 0;
+      sh.m_q = 0;
+      sh.abort = 0;
     }
     __syncthreads();
     const uint32_t j = s_job;
     if (j >= n_big + n_small) break;
     const Lz4Job job = jobs[j < n_big ? j : n_pages - 1 - (j - n_big)];
-    if (job.clen == 0) {
-      if (job.dlen != 0 && threadIdx.x == 0) atomicCAS(status + job.page, 0, int(SB_EXTERNAL));
+    int rc = 0;
+    if (job.clen == 0 || job.dlen == 0) {
+      // an empty block decodes to nothing; LZ4_decompress_safe rejects everything else here
+      if (!(job.dlen == 0 && job.clen == 1 && job.src[0] == 0) && !(job.clen == 0 && job.dlen == 0)) rc = SB_EXTERNAL;
     } else if (warp == 0) {
-      int rc = lz4_pair_produce(job.src, job.clen, job.dlen, &sh);
-      if (rc && lane == 0) atomicCAS(status + job.page, 0, rc);
+      rc = lz4_scan(job.src, job.clen, &sh);
     } else {
-      lz4_pair_consume(job.dst, &sh);
+      rc = lz4_move(job.dst, job.dlen, uint32_t(uintptr_t(job.src) & 15) + job.clen, &sh);
     }
+    if (rc && lane == 0) atomicCAS(status + job.page, 0, rc);
     __syncthreads();
   }
 }

@@ -141,42 +141,47 @@ template <class Out> __device__ int lz4_decode_warp2(const uint8_t *src, uint32_
 }
 
 // ------------------------------------------------------------------------------------
-// Warp-PAIR streaming decoder of the dedicated LZ4 kernel (one CTA of 64 threads per page).
+// Streaming decoder of the dedicated LZ4 kernel: one CTA of 2 warps per block (page).
 //
-// An LZ4 block is two dependent chains: the token chain (where does the next sequence
-// start) and the match chain (a match may read what the previous match wrote).  One warp
-// walking both pays ~100 dependent instructions per sequence.  Here they run on two warps:
+// Measured on B200 (profiles/README.md): a warp that walks tokens AND moves bytes retires one
+// dependent instruction every ~7-10 cycles and needs ~100 of them per sequence, whatever the
+// lane count -- short sequences (2 literals + 6 match bytes are typical for numeric columns)
+// leave 30 of 32 lanes idle.  So the work is split by what is serial and what is not:
 //
-//   producer (warp 0): input ring (global -> shared, cp.async prefetched), token walk,
-//                      literal bytes straight into the shared output ring, one 8-byte
-//                      descriptor {mpos, offset | ml << 16} per match into a shared queue;
-//                      validates the stream (the consumer trusts descriptors).
-//   consumer (warp 1): pops descriptors 32 at a time (one coalesced load, then shuffles),
-//                      executes the match copies inside the ring and writes the ring behind
-//                      to HBM in 16-byte vectors.
+//   scanner (warp 0): owns the input ring (global -> shared, cp.async).  Finds sequence
+//     starts.  Every lane treats "its" byte of a 32-byte window as a token and computes
+//     where the next token would be; the real chain is then followed with ONE SHFL per
+//     sequence (no memory access on the chain).  Emits one queue entry per sequence = stream
+//     position of its token.  Tokens with length-extension bytes and the block tail take a
+//     scalar path.
+//   mover (warp 1): owns the output ring (shared, written behind to HBM in 16-byte vectors).
+//     Takes up to 32 entries at a time, ONE SEQUENCE PER LANE: every lane parses its token,
+//     a warp scan of the sequence lengths gives every lane its output position, all literals
+//     are copied at once, then the matches run lane-parallel in "independent prefix" rounds:
+//     all leading matches whose source ends before the first pending match begins are copied
+//     concurrently; a match that depends on a pending one starts the next round.  Long
+//     literals / matches are moved by the whole warp.
 //
-// Per sequence the producer's chain is token LDS -> 3 ALU -> next token LDS, the consumer's
-// is source LDS -> STS; everything else is off the critical path.
-//
-// Flow control (shared counters, producer-published `produced`, consumer-published
-// `consumed` / `flushed`):
-//   * queue: the producer writes slot seq only while seq - consumed < SB_LZ4_Q;
-//   * ring : the producer keeps every byte it (or a match it described) writes below
-//            flushed + SB_LZ4_AHEAD, so ring bytes at distance <= SB_LZ4_NEAR behind any
-//            match stay intact; older match sources come from the flushed global output.
+// Shared state: entry queue (scanner -> mover), `produced` / `in_ready` (scanner-published),
+// `consumed` / `m_q` (mover-published; m_q = first stream byte the mover still needs, so the
+// scanner never refills ring slots under it), `abort`.
+// A sequence whose literal or match length needs more than 4 extension bytes (>= 1035) is a
+// BIG entry: it may not fit the rings, so both warps parse and move it in streaming fashion.
 // ------------------------------------------------------------------------------------
-constexpr uint32_t SB_LZ4_Q = 128;                             // descriptor queue entries
-constexpr uint32_t SB_LZ4_AHEAD = 4096;                        // producer lead over `flushed`
-constexpr uint32_t SB_LZ4_NEAR = SB_LZ4_RING - SB_LZ4_AHEAD;   // ring-resident match distance
-constexpr uint32_t SB_LZ4_FLUSHQ = 1024;                       // consumer write-behind granularity
-enum { LZ4_D_END = 1, LZ4_D_ADVANCE = 2, LZ4_D_ERROR = 3 };    // control descriptors (offset == 0)
+constexpr uint32_t SB_LZ4_INR = 4096;       // input ring bytes
+constexpr uint32_t SB_LZ4_INCH = 1024;      // refill granularity
+constexpr uint32_t SB_LZ4_Q = 256;          // queue entries (u32 each)
+constexpr uint32_t SB_LZ4_NEAR = SB_LZ4_RING - 2048 - 64; // match distance served from the ring
+constexpr uint32_t SB_LZ4_FLUSHQ = 1024;    // write-behind granularity
+constexpr uint32_t SB_LZ4_SMALL = 24;       // literal / match lengths handled one sequence per lane
+constexpr uint32_t SB_LZ4_MAXPOS = 0x3fffffffu; // stream / output positions fit 30 bits
+enum { LZ4_E_SEQ = 0u, LZ4_E_END = 1u, LZ4_E_BIG = 2u, LZ4_E_ERROR = 3u }; // entry >> 30
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -185,232 +190,250 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t lds_vol(const uint32_t *p) {
+__device__ __forceinline__ uint32_t lds_vol(uint32_t a) {
   uint32_t v;
-  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
-__device__ __forceinline__ void sts_vol(uint32_t *p, uint32_t v) {
-  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+__device__ __forceinline__ void sts_vol(uint32_t a, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
-struct __align__(16) Lz4PairShared {
+struct __align__(16) Lz4Shared {
   uint8_t out[SB_LZ4_RING];
-  uint8_t in[SB_LZ4_IN];
-  uint2 desc[SB_LZ4_Q];
-  uint32_t produced; // descriptors published by the producer
-  uint32_t consumed; // descriptors retired by the consumer
-  uint32_t flushed;  // output bytes written behind to HBM
-  uint32_t pad;
+  uint8_t in[SB_LZ4_INR];
+  uint32_t q[SB_LZ4_Q];
+  uint32_t produced; // entries published by the scanner
+  uint32_t in_ready; // stream bytes [.., in_ready) are in the input ring
+  uint32_t consumed; // entries retired by the mover
+  uint32_t m_q;      // the mover no longer needs stream bytes below m_q
+  uint32_t abort;    // either side gave up (corrupt stream)
+  uint32_t pad[3];
 };
 
-// input half: global -> shared ring, 1 KiB chunks, one chunk of prefetch in flight
-struct Lz4In {
-  const uint8_t *gal; // 16-byte aligned global base of the compressed stream
-  uint32_t total;     // aligned stream bytes (multiple of 16)
-  uint8_t *in;        // shared input ring
-  uint32_t issued;    // stream bytes requested so far
-  uint32_t ready;     // stream bytes known complete
-  __device__ __forceinline__ void issue_chunk() {
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t end = min(total, issued + SB_LZ4_CHUNK);
-    for (uint32_t o = issued + lane * 16; o < end; o += 512) cp_async16(in + (o & (SB_LZ4_IN - 1)), gal + o);
-    cp_async_commit();
-    issued = end;
-  }
-  // make stream bytes [.., q_end) readable; keeps one chunk of prefetch in flight
-  __device__ __forceinline__ void ensure(uint32_t q, uint32_t q_end) {
-    if (issued < total && q + SB_LZ4_CHUNK >= issued) { // the half before `q`'s half is free again
-      __syncwarp();
-      issue_chunk();
-    }
-    if (q_end > ready) {
-      cp_async_wait_all();
-      __syncwarp();
-      ready = issued;
-    }
-  }
-  __device__ __forceinline__ uint32_t ib(uint32_t q) const { return in[q & (SB_LZ4_IN - 1)]; }
-};
+// ---- scanner -------------------------------------------------------------------------
+struct Lz4Scan {
+  uint32_t sh_b;      // shared address of Lz4Shared
+  const uint8_t *gal; // 16-byte aligned global base of the stream
+  uint32_t total;     // aligned stream bytes
+  uint32_t issued, ready;
+  uint32_t seq, pub;  // entries written / published
+  uint32_t ready_pub; // in_ready as last published
+  uint32_t own;       // lowest stream byte the scanner itself still reads
+  uint32_t c_seen, mq_seen;
 
-// ---- producer ------------------------------------------------------------------------
-struct Lz4Producer {
-  Lz4PairShared *sh;
-  uint32_t seq;      // descriptors written
-  uint32_t c_seen;   // last `consumed` read
-  uint32_t f_seen;   // last `flushed` read
+  __device__ __forceinline__ uint32_t a_in() const { return sh_b + offsetof(Lz4Shared, in); }
+  __device__ __forceinline__ uint32_t ib(uint32_t q) const { return lds_u8(a_in() + (q & (SB_LZ4_INR - 1))); }
   __device__ __forceinline__ void publish() {
-    __threadfence_block();
-    if ((threadIdx.x & 31) == 0) sts_vol(&sh->produced, seq);
-  }
-  // Wait until the queue has `slots` free entries and output bytes below `op_end` may be
-  // written.  When it has to wait it waits for real room (half the queue, 1 KiB of ring) so
-  // the two warps exchange work in large batches instead of ping-ponging per sequence; the
-  // idle consumer always satisfies it: consumed == seq and flushed > op - FLUSHQ - 16.
-  __device__ __forceinline__ void wait_room(uint32_t slots, uint32_t op_end) {
-    if (seq + slots - c_seen <= SB_LZ4_Q && op_end <= f_seen + SB_LZ4_AHEAD) return;
-    publish();
-    for (;;) {
-      c_seen = lds_vol(&sh->consumed);
-      f_seen = lds_vol(&sh->flushed);
-      if (seq + slots - c_seen <= SB_LZ4_Q / 2 && op_end + 1024 <= f_seen + SB_LZ4_AHEAD) break;
-      __nanosleep(32);
+    fence_cta();
+    if ((threadIdx.x & 31) == 0) {
+      sts_vol(sh_b + offsetof(Lz4Shared, in_ready), ready);
+      sts_vol(sh_b + offsetof(Lz4Shared, produced), seq);
     }
+    pub = seq;
+    ready_pub = ready;
   }
-  __device__ __forceinline__ void push(uint32_t x, uint32_t y) { // room must have been waited for
-    if ((threadIdx.x & 31) == 0) sh->desc[seq & (SB_LZ4_Q - 1)] = make_uint2(x, y);
+  __device__ __forceinline__ void refresh() {
+    c_seen = lds_vol(sh_b + offsetof(Lz4Shared, consumed));
+    mq_seen = lds_vol(sh_b + offsetof(Lz4Shared, m_q));
+  }
+  __device__ __forceinline__ bool aborted() const { return lds_vol(sh_b + offsetof(Lz4Shared, abort)) != 0; }
+  // request every chunk whose ring slots the mover (and the scanner itself) has released
+  __device__ __forceinline__ bool issue_allowed() {
+    const uint32_t lane = threadIdx.x & 31;
+    bool any = false;
+    // the chunk at `issued` lands on the ring slots of stream bytes [issued - INR, issued - INR + INCH)
+    while (issued < total && (issued < SB_LZ4_INR || min(mq_seen, own) + (SB_LZ4_INR - SB_LZ4_INCH) >= issued)) {
+      uint32_t end = min(total, issued + SB_LZ4_INCH);
+      for (uint32_t o = issued + lane * 16; o < end; o += 512) cp_async16(a_in() + (o & (SB_LZ4_INR - 1)), gal + o);
+      issued = end;
+      any = true;
+    }
+    if (any) cp_async_commit();
+    return any;
+  }
+  // make stream bytes [.., upto) readable (upto <= total).  false = aborted by the mover.
+  __device__ bool need(uint32_t upto) {
+    upto = min(upto, total);
+    while (ready < upto) {
+      if (issued > ready) {
+        cp_async_wait_all();
+        __syncwarp();
+        ready = issued;
+        publish(); // the mover may be streaming a long run: tell it right away
+        if (ready >= upto) break;
+      }
+      refresh();
+      if (issue_allowed()) continue;
+      publish(); // blocked on the mover: everything found so far must be visible to it
+      if (aborted()) return false;
+      __nanosleep(64);
+    }
+    return true;
+  }
+  // room for `n` more entries
+  __device__ bool room(uint32_t n) {
+    while (seq + n - c_seen > SB_LZ4_Q) {
+      refresh();
+      if (seq + n - c_seen <= SB_LZ4_Q) break;
+      publish();
+      if (aborted()) return false;
+      __nanosleep(64);
+    }
+    return true;
+  }
+  __device__ __forceinline__ void push(uint32_t q, uint32_t kind) { // room must exist
+    if ((threadIdx.x & 31) == 0) sts_vol(sh_b + offsetof(Lz4Shared, q) + ((seq & (SB_LZ4_Q - 1)) << 2), q | (kind << 30));
     ++seq;
   }
 };
 
-__device__ int lz4_pair_produce(const uint8_t *src, uint32_t clen, uint32_t dlen, Lz4PairShared *sh) {
+// Returns 0 or SB_EXTERNAL.  The scanner validates the shape of the stream (every token, length
+// byte and offset inside the block); the mover validates offsets and output sizes.
+__device__ int lz4_scan(const uint8_t *src, uint32_t clen, Lz4Shared *sh) {
   const uint32_t lane = threadIdx.x & 31;
-  constexpr uint32_t IM = SB_LZ4_IN - 1, OM = SB_LZ4_RING - 1;
-  Lz4In s;
+  constexpr uint32_t IM = SB_LZ4_INR - 1;
+  Lz4Scan s;
+  s.sh_b = smem_u32(sh);
   const uint32_t mis = uint32_t(uintptr_t(src) & 15);
   s.gal = src - mis;
   s.total = (mis + clen + 15) & ~15u;
-  s.in = sh->in;
-  s.issued = 0;
-  s.ready = 0;
-  s.issue_chunk();
-  if (s.issued < s.total) s.issue_chunk();
-  Lz4Producer pr{sh, 0, 0, 0};
-  const uint32_t in_b = smem_u32(sh->in), out_b = smem_u32(sh->out), desc_b = smem_u32(sh->desc);
-  uint32_t ip = 0, op = 0;
-  uint32_t ip_lim = 0, op_lim = 0, seq_lim = 0; // housekeeping is due when a limit is reached
-  uint32_t tok = 0, b = 0;
-  bool reload = true;
+  s.issued = s.ready = s.ready_pub = 0;
+  s.seq = s.pub = 0;
+  s.c_seen = s.mq_seen = 0;
+  s.own = mis;
+  const uint32_t in_b = s.a_in(), q_b = s.sh_b + offsetof(Lz4Shared, q);
+  const uint32_t end = mis + clen; // stream positions are offsets from gal
+  uint32_t q = mis;
+  uint32_t q_lim = 0; // windows run while q < q_lim
   int rc = 0;
+  s.issue_allowed();
   for (;;) {
-    if (ip >= ip_lim || op >= op_lim || pr.seq >= seq_lim || reload) {
-      // ---- housekeeping: input prefetch / completion, flow control against the consumer
-      if (ip >= clen) {
-        rc = SB_EXTERNAL;
+    if (q >= q_lim || s.seq + 12 - s.c_seen > SB_LZ4_Q) {
+      // ---- housekeeping: completed prefetches, new prefetches, queue room
+      if (s.issued > s.ready) {
+        cp_async_wait_all();
+        __syncwarp();
+        s.ready = s.issued;
+      }
+      s.own = q;
+      s.refresh();
+      s.issue_allowed();
+      if (s.seq - s.pub >= 32 || s.ready != s.ready_pub) s.publish();
+      if (!s.room(12) || !s.need(min(end, q + 64))) {
+        rc = -1; // aborted by the mover (it reports the status)
         break;
       }
-      uint32_t q = mis + ip;
-      s.ensure(q, min(s.total, q + 48));
-      pr.wait_room(1, op + 48);
-      ip_lim = (s.ready >= s.total) ? 0xffffffffu : min(s.ready - 48, s.issued - SB_LZ4_CHUNK) - mis;
-      op_lim = pr.f_seen + SB_LZ4_AHEAD - 47; // fast sequences write at most 33 bytes
-      seq_lim = pr.c_seen + SB_LZ4_Q;
-      tok = lds_u8(in_b + (q & IM));
-      b = lds_u8(in_b + ((q + 1 + lane) & IM));
-      reload = false;
+      // windows need 48 readable bytes and stay clear of the last 64 bytes of the block
+      uint32_t lim_ready = s.ready >= 48 ? s.ready - 48 : 0, lim_end = end >= 64 ? end - 64 : 0;
+      q_lim = min(min(lim_ready, lim_end), q + SB_LZ4_INCH);
     }
-    uint32_t lit = tok >> 4, mlc = tok & 15u;
-    uint32_t nip = ip + 3 + lit;
-    if (lit != 15 && mlc != 15 && nip <= clen) {
-      // ---- fast sequence: token, <= 14 literals and the offset sit in the lane window
-      uint32_t nq = mis + nip;
-      uint32_t tok_n = lds_u8(in_b + (nq & IM));
-      uint32_t b_n = lds_u8(in_b + ((nq + 1 + lane) & IM));
-      uint32_t offset = __shfl_sync(0xffffffffu, b, lit) | (__shfl_sync(0xffffffffu, b, lit + 1) << 8);
-      uint32_t ml = mlc + 4;
-      uint32_t mpos = op + lit, nop = mpos + ml;
-      if (lane < lit) sts_u8(out_b + ((op + lane) & OM), b);
-      if (nop > dlen || offset == 0 || offset > mpos) {
-        rc = SB_EXTERNAL;
-        break;
+    if (q < q_lim) {
+      // ---- window: lane i decodes byte q+i as a token; the chain hops with one SHFL per token
+      const uint32_t b = lds_u8(in_b + ((q + lane) & IM));
+      const uint32_t lit = b >> 4;
+      const uint32_t pack = (lane + 3 + lit) | ((lit == 15 || (b & 15u) == 15) ? 0x100u : 0u);
+      uint32_t p = 0, cnt = 0, myp = 0;
+#pragma unroll
+      for (uint32_t h = 0; h < 11; ++h) { // a sequence takes >= 3 stream bytes: <= 11 tokens in 32 bytes
+        const uint32_t v = __shfl_sync(0xffffffffu, pack, p);
+        if (v & 0x100u) break; // length bytes follow this token: scalar path
+        if (lane == h) myp = p;
+        p = v & 0xffu;
+        cnt = h + 1;
+        if (p >= 32) break;
       }
-      if (lane == 0) {
-        uint32_t y = offset | (ml << 16);
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(desc_b + ((pr.seq & (SB_LZ4_Q - 1)) << 3)), "r"(mpos), "r"(y)
-                     : "memory");
-      }
-      ++pr.seq;
-      if ((pr.seq & 15u) == 0) pr.publish();
-      ip = nip;
-      op = nop;
-      tok = tok_n;
-      b = b_n;
-      continue;
+      if (lane < cnt) sts_vol(q_b + (((s.seq + lane) & (SB_LZ4_Q - 1)) << 2), q + myp);
+      s.seq += cnt;
+      q += p;
+      if (cnt) continue;
     }
-    // ---- general path: length extensions, long runs, stream tail
-    reload = true;
-    ++ip;
-    if (lit == 15) {
-      uint32_t x = 0;
-      do {
-        if (ip >= clen) {
-          rc = SB_EXTERNAL;
+    // ---- scalar path: one token with all checks (length bytes, block tail)
+    s.own = q;
+    if (!s.room(1) || !s.need(min(end, q + 32))) {
+      rc = -1;
+      break;
+    }
+    const uint32_t q0 = q;
+    const uint32_t tok = s.ib(q), mlc = tok & 15u;
+    uint32_t lit = tok >> 4, r = q + 1;
+    bool big = false;
+    // length-extension bytes at r; after 4 of them the sequence becomes a BIG entry, which the
+    // mover parses concurrently (it releases ring space as it goes, we keep feeding input)
+    auto ext = [&](uint32_t &len) -> int {
+      uint32_t x = 255, nx = 0;
+      while (x == 255) {
+        if (r >= end) return SB_EXTERNAL;
+        if ((r & 15) == 0 || nx == 0) {
+          if (big) s.own = r;
+          if (!s.need(min(end, r + 16))) return -1;
+        }
+        x = s.ib(r++);
+        len += x;
+        if (len > SB_LZ4_MAXPOS) return SB_EXTERNAL;
+        if (++nx == 4 && x == 255 && !big) {
+          s.push(q0, LZ4_E_BIG);
+          s.publish();
+          big = true;
+        }
+      }
+      return 0;
+    };
+    if (lit == 15 && (rc = ext(lit)) != 0) break;
+    if (lit > end - r) {
+      rc = SB_EXTERNAL;
+      break;
+    }
+    if (r + lit == end) { // last sequence: literals only
+      if (!big) {
+        if (!s.need(end)) {
+          rc = -1;
           break;
         }
-        s.ensure(mis + ip, mis + ip + 1);
-        x = s.ib(mis + ip);
-        ++ip;
-        lit += x;
-      } while (x == 255);
-      if (rc) break;
+        s.push(q0, LZ4_E_END);
+      }
+      s.publish();
+      s.own = 0xffffffffu; // nothing left to scan
+      if (!s.need(end)) rc = -1; // keep feeding the mover until everything is in the ring
+      break;
     }
-    if (ip > clen || lit > clen - ip || lit > dlen - op) {
+    r += lit;
+    if (big) s.own = r; // the mover streams the literal run; we only need what follows it
+    if (end - r < 2) {
       rc = SB_EXTERNAL;
       break;
     }
-    for (uint32_t done = 0; done < lit;) {
-      uint32_t p = min(lit - done, 512u);
-      s.ensure(mis + ip, mis + ip + p);
-      pr.wait_room(1, op + p);
-      for (uint32_t i = lane; i < p; i += 32) sts_u8(out_b + ((op + i) & OM), s.ib(mis + ip + i));
-      __syncwarp();
-      ip += p;
-      op += p;
-      done += p;
-      pr.push(op, LZ4_D_ADVANCE << 16);
-    }
-    if (ip == clen) break; // last sequence carries literals only
-    if (clen - ip < 2) {
-      rc = SB_EXTERNAL;
+    if (!s.need(min(end, r + 32))) {
+      rc = -1;
       break;
     }
-    s.ensure(mis + ip, mis + ip + 2);
-    uint32_t offset = s.ib(mis + ip) | (s.ib(mis + ip + 1) << 8);
-    ip += 2;
-    if (offset == 0 || offset > op) {
-      rc = SB_EXTERNAL;
-      break;
-    }
+    r += 2;
     uint32_t ml = mlc;
-    if (ml == 15) {
-      uint32_t x = 0;
-      do {
-        if (ip >= clen) {
-          rc = SB_EXTERNAL;
-          break;
-        }
-        s.ensure(mis + ip, mis + ip + 1);
-        x = s.ib(mis + ip);
-        ++ip;
-        ml += x;
-      } while (x == 255);
-      if (rc) break;
-    }
-    ml += 4;
-    if (ml > dlen - op) {
+    if (mlc == 15 && (rc = ext(ml)) != 0) break;
+    if (!big) s.push(q0, LZ4_E_SEQ);
+    q = r;
+    if (q >= end) { // a block must end with a literal-only sequence
       rc = SB_EXTERNAL;
       break;
-    }
-    for (uint32_t done = 0; done < ml;) { // long matches travel as pieces (sources precede each piece)
-      uint32_t p = min(ml - done, 1024u);
-      pr.wait_room(1, op + p);
-      pr.push(op, offset | (p << 16));
-      op += p;
-      done += p;
     }
   }
-  if (rc == 0 && op != dlen) rc = SB_EXTERNAL;
-  pr.wait_room(1, 0);
-  pr.push(op, uint32_t(rc ? LZ4_D_ERROR : LZ4_D_END) << 16);
-  pr.publish();
-  return rc;
+  if (rc > 0) {
+    if (s.room(1)) s.push(q, LZ4_E_ERROR);
+    s.publish();
+    if (lane == 0) sts_vol(s.sh_b + offsetof(Lz4Shared, abort), 1u);
+  } else if (rc == 0) {
+    s.publish();
+  }
+  return rc > 0 ? rc : 0;
 }
 
-// ---- consumer ------------------------------------------------------------------------
+// ---- mover ---------------------------------------------------------------------------
 struct Lz4Out {
-  uint8_t *ring; // shared output ring
-  uint8_t *dst;  // global output
-  uint32_t fl;   // bytes [0, fl) written to dst
+  uint32_t out_b; // shared address of the output ring
+  uint8_t *ring;  // generic pointer to the same ring
+  uint8_t *dst;   // global output
+  uint32_t fl;    // bytes [0, fl) written to dst
   bool vec;
   // write ring bytes [fl, upto) behind to HBM.  Non-final flushes move whole 16-byte vectors
   // only (fl stays 16-byte aligned); the final flush also writes the byte tail.
@@ -433,75 +456,287 @@ struct Lz4Out {
     }
     __syncwarp();
   }
-};
-
-__device__ void lz4_pair_consume(uint8_t *dst, Lz4PairShared *sh) {
-  const uint32_t lane = threadIdx.x & 31;
-  constexpr uint32_t OM = SB_LZ4_RING - 1;
-  Lz4Out o{sh->out, dst, 0, (uintptr_t(dst) & 15) == 0};
-  const uint32_t out_b = smem_u32(sh->out);
-  uint32_t cons = 0;
-  for (;;) {
-    uint32_t prod;
-    while ((prod = lds_vol(&sh->produced)) == cons) __nanosleep(20);
-    __threadfence_block();
-    uint32_t nb = min(prod - cons, 32u);
-    uint2 d = make_uint2(0, 0);
-    if (lane < nb) d = sh->desc[(cons + lane) & (SB_LZ4_Q - 1)];
-    for (uint32_t k = 0; k < nb; ++k) {
-      uint32_t mpos = __shfl_sync(0xffffffffu, d.x, k), y = __shfl_sync(0xffffffffu, d.y, k);
-      uint32_t offset = y & 0xffffu, ml = y >> 16;
-      if (offset == 0) { // control descriptor
-        if (ml == LZ4_D_ADVANCE) {
-          if (mpos - o.fl >= SB_LZ4_FLUSHQ) o.flush_to(mpos, false);
-          continue;
-        }
-        if (ml == LZ4_D_END) o.flush_to(mpos, true);
-        return;
-      }
-      if (ml <= 32 && offset >= ml && offset <= SB_LZ4_NEAR) {
-        // common: source inside the ring, no overlap with the bytes being written
-        if (lane < ml) sts_u8(out_b + ((mpos + lane) & OM), lds_u8(out_b + ((mpos - offset + lane) & OM)));
+  // one earlier output byte for a match at `mpos` (ring when near or not flushed yet)
+  __device__ __forceinline__ uint32_t src_byte(uint32_t sp, uint32_t mpos) const {
+    if (mpos - sp <= SB_LZ4_NEAR || sp >= fl) return lds_u8(out_b + (sp & (SB_LZ4_RING - 1)));
+    return __ldcg(dst + sp);
+  }
+  // whole-warp match copy of `ml` bytes at `mpos` (any length, any overlap)
+  __device__ void match_coop(uint32_t mpos, uint32_t offset, uint32_t ml) {
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr uint32_t OM = SB_LZ4_RING - 1;
+    for (uint32_t done = 0; done < ml;) {
+      uint32_t p = min(ml - done, 1024u), at = mpos + done;
+      if (offset < 32) { // pattern replication: lane byte = pattern[lane % offset]
+        uint32_t v = lds_u8(out_b + ((at - offset + lane % offset) & OM));
+        uint32_t step = 32 - 32 % offset;
         __syncwarp();
-      } else if (offset <= SB_LZ4_NEAR) {
-        // ring-resident, long or self-overlapping: 32-byte steps (a step's sources precede it
-        // when offset >= 32; shorter offsets replicate a pattern: index modulo offset)
-        if (offset >= 32) {
-          for (uint32_t i = 0; i < ml; i += 32) {
-            if (i + lane < ml) sts_u8(out_b + ((mpos + i + lane) & OM), lds_u8(out_b + ((mpos - offset + i + lane) & OM)));
-            __syncwarp();
-          }
-        } else {
-          uint32_t v = lds_u8(out_b + ((mpos - offset + lane % offset) & OM)); // pattern byte of lane
-          uint32_t step = 32 - 32 % offset;                                   // multiple of offset
-          for (uint32_t i = 0; i < ml; i += step)
-            if (lane < step && i + lane < ml) sts_u8(out_b + ((mpos + i + lane) & OM), v);
-          __syncwarp();
-        }
+        for (uint32_t i = 0; i < p; i += step)
+          if (lane < step && i + lane < p) sts_u8(out_b + ((at + i + lane) & OM), v);
+        __syncwarp();
       } else {
-        // far source: read it from the flushed global output
-        if (mpos - offset + min(ml, offset) > o.fl) o.flush_to(mpos, true);
-        for (uint32_t i = 0; i < ml; i += 32) {
-          uint32_t n_i = min(32u, ml - i);
-          // offset > NEAR >= 32: sources of a 32-byte step never overlap its destination,
-          // but may not be flushed yet when offset < ml: those bytes are still in the ring
-          if (lane < n_i) {
-            uint32_t sp = mpos - offset + i + lane;
-            uint32_t v = sp < o.fl ? uint32_t(__ldcg(dst + sp)) : lds_u8(out_b + (sp & OM));
-            sts_u8(out_b + ((mpos + i + lane) & OM), v);
-          }
+        for (uint32_t i = 0; i < p; i += 32) { // a 32-byte step's sources precede it (offset >= 32)
+          if (i + lane < p) sts_u8(out_b + ((at + i + lane) & OM), src_byte(at - offset + i + lane, at));
           __syncwarp();
         }
       }
-      if (mpos + ml - o.fl >= SB_LZ4_FLUSHQ) o.flush_to(mpos + ml, false);
-    }
-    cons += nb;
-    __threadfence_block();
-    if (lane == 0) {
-      sts_vol(&sh->flushed, o.fl);
-      sts_vol(&sh->consumed, cons);
+      done += p;
+      if (at + p - fl >= SB_LZ4_FLUSHQ) flush_to(at + p, false);
     }
   }
+};
+
+// copy n <= SB_LZ4_SMALL bytes, 8 independent loads in flight (source and destination must not
+// overlap within a group of 8: callers guarantee distance >= 8 or disjoint buffers)
+template <class Ld> __device__ __forceinline__ void lz4_copy_small(uint32_t dst_b, uint32_t dpos, uint32_t n, Ld ld) {
+  constexpr uint32_t OM = SB_LZ4_RING - 1;
+  for (uint32_t t0 = 0; t0 < n; t0 += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k)
+      if (t0 + k < n) v[k] = ld(t0 + k);
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k)
+      if (t0 + k < n) sts_u8(dst_b + ((dpos + t0 + k) & OM), v[k]);
+  }
+}
+
+__device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Shared *sh) {
+  const uint32_t lane = threadIdx.x & 31;
+  constexpr uint32_t OM = SB_LZ4_RING - 1, IM = SB_LZ4_INR - 1;
+  const uint32_t sh_b = smem_u32(sh);
+  const uint32_t in_b = sh_b + offsetof(Lz4Shared, in);
+  Lz4Out o;
+  o.out_b = sh_b + offsetof(Lz4Shared, out);
+  o.ring = sh->out;
+  o.dst = dst;
+  o.fl = 0;
+  o.vec = (uintptr_t(dst) & 15) == 0;
+  const uint32_t out_b = o.out_b;
+  uint32_t cons = 0, op_base = 0;
+  int rc = 0;
+  auto wait_in = [&](uint32_t upto) -> bool { // stream bytes [.., upto) in the ring
+    for (;;) {
+      if (lds_vol(sh_b + offsetof(Lz4Shared, in_ready)) >= upto) break;
+      if (lds_vol(sh_b + offsetof(Lz4Shared, abort))) return false;
+      __nanosleep(64);
+    }
+    fence_cta();
+    return true;
+  };
+  auto release_in = [&](uint32_t q) {
+    fence_cta();
+    if (lane == 0) sts_vol(sh_b + offsetof(Lz4Shared, m_q), q);
+  };
+  // whole-warp literal copy of stream bytes [ls, ls+lit) to output position op, streaming
+  auto lit_coop = [&](uint32_t ls, uint32_t lit, uint32_t op, bool stream) -> bool {
+    for (uint32_t done = 0; done < lit;) {
+      uint32_t p = min(lit - done, 512u);
+      if (stream) {
+        release_in(ls + done); // BEFORE waiting: the scanner may need the ring space to deliver
+        if (!wait_in(min(stream_end, ls + done + p))) return false;
+      }
+      for (uint32_t i = lane; i < p; i += 32) sts_u8(out_b + ((op + done + i) & OM), lds_u8(in_b + ((ls + done + i) & IM)));
+      __syncwarp();
+      done += p;
+      if (op + done - o.fl >= SB_LZ4_FLUSHQ) o.flush_to(op + done, false);
+    }
+    if (stream) release_in(ls + lit);
+    return true;
+  };
+  // length-extension bytes at stream position r, read as they arrive (BIG entries)
+  auto ext_stream = [&](uint32_t &r, uint32_t &len) -> int {
+    uint32_t x = 255, avail = 0;
+    while (x == 255) {
+      if (r >= stream_end) return SB_EXTERNAL;
+      if (r >= avail) {
+        release_in(r); // before waiting: the scanner may need the ring space to get further
+        if (!wait_in(r + 1)) return -1;
+        avail = lds_vol(sh_b + offsetof(Lz4Shared, in_ready));
+      }
+      x = lds_u8(in_b + (r++ & IM));
+      len += x;
+      if (len > SB_LZ4_MAXPOS) return SB_EXTERNAL;
+    }
+    return 0;
+  };
+  for (;;) {
+    uint32_t prod;
+    while ((prod = lds_vol(sh_b + offsetof(Lz4Shared, produced))) == cons) {
+      if (lds_vol(sh_b + offsetof(Lz4Shared, abort))) return 0; // the scanner reports
+      __nanosleep(32);
+    }
+    fence_cta();
+    const uint32_t nb = min(prod - cons, 32u);
+    // ---- one sequence per lane: parse
+    uint32_t q = 0, kind = LZ4_E_SEQ, lit = 0, ml = 0, offset = 1, ls = 0, qn = 0;
+    if (lane < nb) {
+      const uint32_t e = sh->q[(cons + lane) & (SB_LZ4_Q - 1)];
+      q = e & SB_LZ4_MAXPOS;
+      kind = e >> 30;
+      const uint32_t tok = lds_u8(in_b + (q & IM));
+      lit = tok >> 4;
+      uint32_t mlc = tok & 15u, r = q + 1;
+      if (kind == LZ4_E_BIG || kind == LZ4_E_ERROR) lit = 0; // BIG: parsed by the whole warp, streaming
+      if (lit == 15) { // at most 4 length bytes (the scanner made longer ones BIG)
+        uint32_t x;
+        do {
+          x = lds_u8(in_b + (r++ & IM));
+          lit += x;
+        } while (x == 255 && r < stream_end);
+      }
+      ls = r;
+      r += lit;
+      if (kind == LZ4_E_SEQ) {
+        offset = lds_u8(in_b + (r & IM)) | (lds_u8(in_b + ((r + 1) & IM)) << 8);
+        r += 2;
+        ml = mlc;
+        if (mlc == 15) {
+          uint32_t x;
+          do {
+            x = lds_u8(in_b + (r++ & IM));
+            ml += x;
+          } while (x == 255 && r < stream_end);
+        }
+        ml += 4;
+      }
+      qn = kind == LZ4_E_SEQ ? r : q;
+    }
+    const uint32_t spec_mask = __ballot_sync(0xffffffffu, lane < nb && kind != LZ4_E_SEQ);
+    uint32_t i = 0;
+    while (i < nb) {
+      const uint32_t spec = spec_mask >> i;
+      const uint32_t e = spec ? i + uint32_t(__ffs(int(spec))) - 1u : nb; // next special entry
+      if (e == i) {
+        // ---- END / BIG / ERROR entry: the whole warp handles it, streaming
+        const uint32_t k_ = __shfl_sync(0xffffffffu, kind, i), q_ = __shfl_sync(0xffffffffu, q, i);
+        uint32_t lit_ = __shfl_sync(0xffffffffu, lit, i), ls_ = __shfl_sync(0xffffffffu, ls, i);
+        if (k_ == LZ4_E_ERROR) {
+          rc = SB_EXTERNAL;
+          break;
+        }
+        const bool big = k_ == LZ4_E_BIG;
+        const uint32_t tok_ = lds_u8(in_b + (q_ & IM)); // before its ring slot is released
+        release_in(q_);                                 // every earlier entry of the batch is done
+        if (big) { // literal length, streaming
+          uint32_t r = q_ + 1;
+          lit_ = tok_ >> 4;
+          if (lit_ == 15 && (rc = ext_stream(r, lit_)) != 0) break;
+          ls_ = r;
+        }
+        if (lit_ > dlen - op_base) {
+          rc = SB_EXTERNAL;
+          break;
+        }
+        if (!lit_coop(ls_, lit_, op_base, true)) {
+          rc = -1;
+          break;
+        }
+        op_base += lit_;
+        if (k_ == LZ4_E_END || ls_ + lit_ == stream_end) { // last sequence of the block
+          if (op_base != dlen) rc = SB_EXTERNAL;
+          else o.flush_to(dlen, true);
+          if (rc && lane == 0) sts_vol(sh_b + offsetof(Lz4Shared, abort), 1u);
+          return rc;
+        }
+        // offset and match length follow the literal run
+        uint32_t r = ls_ + lit_;
+        if (stream_end - r < 2) {
+          rc = SB_EXTERNAL;
+          break;
+        }
+        if (!wait_in(min(stream_end, r + 2))) {
+          rc = -1;
+          break;
+        }
+        const uint32_t off_ = lds_u8(in_b + (r & IM)) | (lds_u8(in_b + ((r + 1) & IM)) << 8);
+        r += 2;
+        uint32_t ml_ = tok_ & 15u;
+        if (ml_ == 15 && (rc = ext_stream(r, ml_)) != 0) break;
+        ml_ += 4;
+        release_in(r);
+        if (off_ == 0 || off_ > op_base || ml_ > dlen - op_base) {
+          rc = SB_EXTERNAL;
+          break;
+        }
+        o.match_coop(op_base, off_, ml_);
+        op_base += ml_;
+        ++i;
+        continue;
+      }
+      // ---- segment [i, e) of ordinary sequences: output positions by a warp scan
+      const bool in_seg = lane >= i && lane < e;
+      const uint32_t len = in_seg ? lit + ml : 0u;
+      const uint32_t incl = warp_incl_scan(len);
+      const uint32_t op = op_base + incl - len, mpos = op + lit;
+      const uint32_t seg_total = __shfl_sync(0xffffffffu, incl, 31);
+      // lengths are < 2^12 each (longer ones are BIG), so the sums cannot wrap
+      const bool bad = in_seg && (offset == 0 || offset > mpos || mpos + ml > dlen);
+      if (__ballot_sync(0xffffffffu, bad)) {
+        rc = SB_EXTERNAL;
+        break;
+      }
+      const uint32_t small_mask = __ballot_sync(0xffffffffu, in_seg && lit <= SB_LZ4_SMALL && ml <= SB_LZ4_SMALL);
+      uint32_t a = i;
+      while (a < e) {
+        if (!(small_mask & (1u << a))) {
+          // a long sequence: the whole warp moves it
+          const uint32_t op_ = __shfl_sync(0xffffffffu, op, a), lit_ = __shfl_sync(0xffffffffu, lit, a);
+          const uint32_t ls_ = __shfl_sync(0xffffffffu, ls, a), off_ = __shfl_sync(0xffffffffu, offset, a);
+          const uint32_t ml_ = __shfl_sync(0xffffffffu, ml, a);
+          lit_coop(ls_, lit_, op_, false);
+          o.match_coop(op_ + lit_, off_, ml_);
+          ++a;
+          continue;
+        }
+        // run [a, j) of short sequences, one per lane
+        const uint32_t rest = small_mask >> a;
+        const uint32_t j = a + (~rest ? uint32_t(__ffs(int(~rest))) - 1u : 32u - a);
+        const bool mine = lane >= a && lane < j;
+        if (mine) lz4_copy_small(out_b, op, lit, [&](uint32_t t) { return lds_u8(in_b + ((ls + t) & IM)); });
+        __syncwarp();
+        // matches in independent-prefix rounds: everything before the first pending match is final
+        uint32_t f = a;
+        while (f < j) {
+          const uint32_t first = __shfl_sync(0xffffffffu, mpos, f);
+          const bool dep = lane > f && (mpos - offset + min(ml, offset) > first);
+          const uint32_t dmask = __ballot_sync(0xffffffffu, dep || lane >= j) & ~((2u << f) - 1u);
+          const uint32_t bnd = dmask ? uint32_t(__ffs(int(dmask))) - 1u : 32u; // first lane not in this round
+          if (lane >= f && lane < bnd) {
+            const uint32_t sp = mpos - offset;
+            if (offset >= 8 || offset >= ml) {
+              if (offset <= SB_LZ4_NEAR) {
+                lz4_copy_small(out_b, mpos, ml, [&](uint32_t t) { return lds_u8(out_b + ((sp + t) & OM)); });
+              } else if (offset > SB_LZ4_NEAR + 32 && sp + ml <= o.fl) { // all of it flushed: L2
+                lz4_copy_small(out_b, mpos, ml, [&](uint32_t t) { return uint32_t(__ldcg(dst + sp + t)); });
+              } else {
+                for (uint32_t t = 0; t < ml; ++t) sts_u8(out_b + ((mpos + t) & OM), o.src_byte(sp + t, mpos));
+              }
+            } else { // short self-overlap: byte by byte
+              for (uint32_t t = 0; t < ml; ++t) sts_u8(out_b + ((mpos + t) & OM), lds_u8(out_b + ((sp + t) & OM)));
+            }
+          }
+          __syncwarp();
+          f = min(bnd, j);
+        }
+        const uint32_t op_end = __shfl_sync(0xffffffffu, mpos + ml, j - 1);
+        if (op_end - o.fl >= SB_LZ4_FLUSHQ) o.flush_to(op_end, false);
+        a = j;
+      }
+      op_base += seg_total;
+      i = e;
+    }
+    if (rc) break;
+    cons += nb;
+    const uint32_t q_next = __shfl_sync(0xffffffffu, qn, nb - 1);
+    fence_cta();
+    if (lane == 0) {
+      sts_vol(sh_b + offsetof(Lz4Shared, m_q), q_next);
+      sts_vol(sh_b + offsetof(Lz4Shared, consumed), cons);
+    }
+  }
+  if (lane == 0) sts_vol(sh_b + offsetof(Lz4Shared, abort), 1u);
+  return rc > 0 ? rc : 0;
 }
 
 } // namespace sb
