@@ -168,6 +168,8 @@ typedef struct {
   uint64_t codec_pages[32]; /* pages per top-level codec id */
   float main_kernel_ms;    /* decode: sb_decode_kernel (pass 1) alone */
   float lz4_kernel_ms;     /* decode: sb_lz4_kernel alone (runs concurrently with the main kernel) */
+  uint64_t lz4_bytes;      /* decode: compressed + decoded bytes of the blocks sb_lz4_kernel handled */
+  float host_ms;           /* wall time of the whole call on the host */
 } sb_stats;
 int32_t sb_last_stats(const sb_ctx *ctx, sb_stats *out);
 

@@ -97,7 +97,9 @@ class Decoded:
         self.type = type_
         self.length = int(out.length)
         self.mem = out.mem
-        self.page_status = [out.page_status[i] for i in range(group.n_pages[idx])]
+        npg = group.n_pages[idx]
+        # one bulk copy (a Python loop over 10^4 pages would dominate a decode call)
+        self.page_status = (np.ctypeslib.as_array(out.page_status, shape=(npg,)).copy() if npg else np.zeros(0, np.int32))
         self._group = group
         self.values_ptr, self.values_bytes = out.values, int(out.values_bytes)
         self.offsets_ptr, self.offsets_bytes = out.offsets, int(out.offsets_bytes)
@@ -193,6 +195,7 @@ class Context:
         return {"pages": s.pages, "bytes_in": s.bytes_in, "bytes_out": s.bytes_out,
                 "kernel_launches": s.kernel_launches, "device_ms": s.device_ms,
                 "main_kernel_ms": s.main_kernel_ms, "lz4_kernel_ms": s.lz4_kernel_ms,
+                "lz4_bytes": s.lz4_bytes, "host_ms": s.host_ms,
                 "codec_pages": {i: s.codec_pages[i] for i in range(32) if s.codec_pages[i]}}
 
     # ---- decode ----------------------------------------------------------------------

@@ -46,7 +46,8 @@ class ColumnOut(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("pages", C.c_uint64), ("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("device_ms", C.c_float), ("codec_pages", C.c_uint64 * 32),
-                ("main_kernel_ms", C.c_float), ("lz4_kernel_ms", C.c_float)]
+                ("main_kernel_ms", C.c_float), ("lz4_kernel_ms", C.c_float),
+                ("lz4_bytes", C.c_uint64), ("host_ms", C.c_float)]
 
 
 class WriteOptions(C.Structure):

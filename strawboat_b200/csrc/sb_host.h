@@ -34,6 +34,8 @@ struct sb_ctx {
   cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr, ev_lz0 = nullptr, ev_lz1 = nullptr; // per-kernel timing
   int sm_count = 0;
   int max_smem_optin = 0;
+  int lz4_occ = 0, occ_val = 0; // cached occupancy queries
+  uint32_t occ_smem = 0;
   DevBuf d_tables, d_scratch, d_entries;
   void *h_tables = nullptr;
   size_t h_tables_cap = 0;

@@ -8,6 +8,7 @@
 //          load of the page into shared memory, codec dispatch, coalesced 16-byte stores
 // There is no CPU fallback anywhere: without a CUDA device every entry point returns SB_CUDA.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -110,7 +111,7 @@ __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const Col
 
 __global__ void __launch_bounds__(64, 16)
     sb_lz4_kernel(const Lz4Job *__restrict__ jobs, const uint32_t *__restrict__ n_jobs_p, uint32_t n_pages, uint32_t *counter,
-                  int32_t *status) {
+                  int32_t *status, unsigned long long *bytes_done) {
   __shared__ Lz4Shared sh;
   __shared__ uint32_t s_job;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(64, 16)
       rc = lz4_move(job.dst, job.dlen, uint32_t(uintptr_t(job.src) & 15) + job.clen, &sh);
     }
     if (rc && lane == 0) atomicCAS(status + job.page, 0, rc);
+    if (threadIdx.x == 0) atomicAdd(bytes_done, (unsigned long long)(job.clen) + job.dlen);
     __syncthreads();
   }
 }
@@ -413,6 +415,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   cudaStream_t st = ctx->stream;
   std::memset(outs, 0, sizeof(sb_column_out) * n_cols);
   ctx->stats = sb_stats{};
+  const auto t_host0 = std::chrono::steady_clock::now();
 
   // ---- host pass: validate, count pages / work items
   uint64_t n_pages_total = 0, n_items = 0, n_plan = 0, n_entries = 0, max_elems_bytes = 0;
@@ -615,16 +618,20 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   // ---- launch configuration
   uint32_t smem = uint32_t(align_up(std::min<uint64_t>(uint64_t(max_stage) + 48, stage_cap) + kArenaMin, 1024));
   smem = std::min(std::max(smem, kSmemMin), kSmemMax);
-  int occ = 1;
-  SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_decode_kernel, SB_NT, smem));
-  occ = std::max(1, occ);
+  if (ctx->occ_smem != smem) { // occupancy queries cost tens of microseconds: once per shared-memory size
+    int q = 1;
+    SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, sb_decode_kernel, SB_NT, smem));
+    ctx->occ_smem = smem;
+    ctx->occ_val = std::max(1, q);
+  }
+  const int occ = ctx->occ_val;
   uint32_t grid = uint32_t(std::min<uint64_t>(std::max<uint64_t>(n_items, 1), uint64_t(ctx->sm_count) * occ));
   uint64_t scratch_per_cta = align_up(3 * (max_elems_bytes + 64) + 16 * 1024, 256);
   const PageDesc *d_pages = reinterpret_cast<const PageDesc *>(dT + off_pages);
   const ColDesc *d_cols = reinterpret_cast<const ColDesc *>(dT + off_cols);
   int32_t *d_status = reinterpret_cast<int32_t *>(dT + off_status);
   // counters: [0] main queue, [1] lz4 queue, [2] long lz4 jobs, [3] short lz4 jobs, [4] plan queue,
-  //           [5..36] pages per top-level codec
+  //           [5..36] pages per top-level codec, [38..39] u64 bytes handled by sb_lz4_kernel
   uint32_t *d_counters = reinterpret_cast<uint32_t *>(dT + off_counters);
   uint8_t *d_flags = dT + off_flags;
   Lz4Job *d_jobs = reinterpret_cast<Lz4Job *>(dT + off_jobs);
@@ -720,11 +727,16 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
                                                                               d_counters + 2, d_flags);
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_fork, st));
       SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-      int lz4_occ = 1;
-      SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz4_occ, sb_lz4_kernel, 64, 0));
+      if (ctx->lz4_occ == 0) {
+        int q = 1;
+        SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, sb_lz4_kernel, 64, 0));
+        ctx->lz4_occ = std::max(1, q);
+      }
+      const int lz4_occ = ctx->lz4_occ;
       uint32_t lz4_grid = uint32_t(std::min<uint64_t>(n_pages_total, uint64_t(ctx->sm_count) * std::max(1, lz4_occ)));
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_lz0, ctx->aux));
-      sb_lz4_kernel<<<lz4_grid, 64, 0, ctx->aux>>>(d_jobs, d_counters + 2, uint32_t(n_pages_total), d_counters + 1, d_status);
+      sb_lz4_kernel<<<lz4_grid, 64, 0, ctx->aux>>>(d_jobs, d_counters + 2, uint32_t(n_pages_total), d_counters + 1, d_status,
+                                                   reinterpret_cast<unsigned long long *>(d_counters + 38));
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_lz1, ctx->aux));
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
       ctx->stats.kernel_launches += 2;
@@ -791,7 +803,10 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   const int32_t *h_status = reinterpret_cast<const int32_t *>(hT + off_status);
   const uint32_t *h_counters = reinterpret_cast<const uint32_t *>(hT + off_counters);
   if (n_items)
+  {
     for (int i = 0; i < 32; ++i) ctx->stats.codec_pages[i] = h_counters[5 + i];
+    std::memcpy(&ctx->stats.lz4_bytes, h_counters + 38, 8);
+  }
   pi = 0;
   for (uint64_t c = 0; c < n_cols; ++c) {
     sb_column_out &o = outs[c];
@@ -807,6 +822,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       }
     }
   }
+  ctx->stats.host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
   ctx->stats.pages = n_pages_total;
   ctx->stats.bytes_in = bytes_in;
   ctx->stats.bytes_out = bytes_out;

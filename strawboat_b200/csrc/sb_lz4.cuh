@@ -173,7 +173,7 @@ constexpr uint32_t SB_LZ4_INCH = 1024;      // refill granularity
 constexpr uint32_t SB_LZ4_Q = 256;          // queue entries (u32 each)
 constexpr uint32_t SB_LZ4_NEAR = SB_LZ4_RING - 2048 - 64; // match distance served from the ring
 constexpr uint32_t SB_LZ4_FLUSHQ = 1024;    // write-behind granularity
-constexpr uint32_t SB_LZ4_SMALL = 24;       // literal / match lengths handled one sequence per lane
+constexpr uint32_t SB_LZ4_SMALL = 16;       // literal / match lengths handled one sequence per lane
 constexpr uint32_t SB_LZ4_MAXPOS = 0x3fffffffu; // stream / output positions fit 30 bits
 enum { LZ4_E_SEQ = 0u, LZ4_E_END = 1u, LZ4_E_BIG = 2u, LZ4_E_ERROR = 3u }; // entry >> 30
 
@@ -279,7 +279,7 @@ struct Lz4Scan {
       if (seq + n - c_seen <= SB_LZ4_Q) break;
       publish();
       if (aborted()) return false;
-      __nanosleep(64);
+      __nanosleep(256);
     }
     return true;
   }
@@ -486,18 +486,70 @@ struct Lz4Out {
   }
 };
 
-// copy n <= SB_LZ4_SMALL bytes, 8 independent loads in flight (source and destination must not
-// overlap within a group of 8: callers guarantee distance >= 8 or disjoint buffers)
-template <class Ld> __device__ __forceinline__ void lz4_copy_small(uint32_t dst_b, uint32_t dpos, uint32_t n, Ld ld) {
-  constexpr uint32_t OM = SB_LZ4_RING - 1;
-  for (uint32_t t0 = 0; t0 < n; t0 += 8) {
-    uint32_t v[8];
-#pragma unroll
-    for (uint32_t k = 0; k < 8; ++k)
-      if (t0 + k < n) v[k] = ld(t0 + k);
-#pragma unroll
-    for (uint32_t k = 0; k < 8; ++k)
-      if (t0 + k < n) sts_u8(dst_b + ((dpos + t0 + k) & OM), v[k]);
+// Per-lane copy of bytes [K, K+4) of a short run, predicated on k < n.  Register + immediate
+// addressing, no per-byte address arithmetic: 4 SETP + 4 loads + 4 stores.  The caller
+// guarantees that neither range wraps around its ring and that the source bytes of one group
+// are not written by the same group (distance >= 4 or disjoint buffers).
+template <int K> __device__ __forceinline__ void lz4_copy4_ss(uint32_t s, uint32_t d, uint32_t n) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p<4>;\n\t"
+      ".reg .u32 v<4>;\n\t"
+      "setp.gt.u32 p0, %2, %3;\n\t"
+      "setp.gt.u32 p1, %2, %4;\n\t"
+      "setp.gt.u32 p2, %2, %5;\n\t"
+      "setp.gt.u32 p3, %2, %6;\n\t"
+      "@p0 ld.shared.u8 v0, [%0+%3];\n\t"
+      "@p1 ld.shared.u8 v1, [%0+%4];\n\t"
+      "@p2 ld.shared.u8 v2, [%0+%5];\n\t"
+      "@p3 ld.shared.u8 v3, [%0+%6];\n\t"
+      "@p0 st.shared.u8 [%1+%3], v0;\n\t"
+      "@p1 st.shared.u8 [%1+%4], v1;\n\t"
+      "@p2 st.shared.u8 [%1+%5], v2;\n\t"
+      "@p3 st.shared.u8 [%1+%6], v3;\n\t"
+      "}" ::"r"(s),
+      "r"(d), "r"(n), "n"(K), "n"(K + 1), "n"(K + 2), "n"(K + 3)
+      : "memory");
+}
+template <int K> __device__ __forceinline__ void lz4_copy4_gs(const uint8_t *s, uint32_t d, uint32_t n) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p<4>;\n\t"
+      ".reg .u32 v<4>;\n\t"
+      "setp.gt.u32 p0, %2, %3;\n\t"
+      "setp.gt.u32 p1, %2, %4;\n\t"
+      "setp.gt.u32 p2, %2, %5;\n\t"
+      "setp.gt.u32 p3, %2, %6;\n\t"
+      "@p0 ld.global.cg.u8 v0, [%0+%3];\n\t"
+      "@p1 ld.global.cg.u8 v1, [%0+%4];\n\t"
+      "@p2 ld.global.cg.u8 v2, [%0+%5];\n\t"
+      "@p3 ld.global.cg.u8 v3, [%0+%6];\n\t"
+      "@p0 st.shared.u8 [%1+%3], v0;\n\t"
+      "@p1 st.shared.u8 [%1+%4], v1;\n\t"
+      "@p2 st.shared.u8 [%1+%5], v2;\n\t"
+      "@p3 st.shared.u8 [%1+%6], v3;\n\t"
+      "}" ::"l"(s),
+      "r"(d), "r"(n), "n"(K), "n"(K + 1), "n"(K + 2), "n"(K + 3)
+      : "memory");
+}
+// n <= 16 bytes per lane (n = 0 for lanes that do not take part); whole-warp call: the upper
+// groups are skipped when no lane needs them
+__device__ __forceinline__ void lz4_copy16_ss(uint32_t s, uint32_t d, uint32_t n) {
+  lz4_copy4_ss<0>(s, d, n);
+  if (__any_sync(0xffffffffu, n > 4)) {
+    lz4_copy4_ss<4>(s, d, n);
+    if (__any_sync(0xffffffffu, n > 8)) {
+      lz4_copy4_ss<8>(s, d, n);
+      lz4_copy4_ss<12>(s, d, n);
+    }
+  }
+}
+__device__ __forceinline__ void lz4_copy16_gs(const uint8_t *s, uint32_t d, uint32_t n) {
+  lz4_copy4_gs<0>(s, d, n);
+  lz4_copy4_gs<4>(s, d, n);
+  if (__any_sync(0xffffffffu, n > 8)) {
+    lz4_copy4_gs<8>(s, d, n);
+    lz4_copy4_gs<12>(s, d, n);
   }
 }
 
@@ -693,29 +745,33 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
         const uint32_t rest = small_mask >> a;
         const uint32_t j = a + (~rest ? uint32_t(__ffs(int(~rest))) - 1u : 32u - a);
         const bool mine = lane >= a && lane < j;
-        if (mine) lz4_copy_small(out_b, op, lit, [&](uint32_t t) { return lds_u8(in_b + ((ls + t) & IM)); });
+        const uint32_t sp = mpos - offset;
+        const uint32_t d_lit = op & OM, s_lit = ls & IM, d_m = mpos & OM, s_m = sp & OM;
+        // literals of the whole run at once
+        {
+          const bool lean = mine && s_lit + lit <= SB_LZ4_INR && d_lit + lit <= SB_LZ4_RING;
+          lz4_copy16_ss(in_b + s_lit, out_b + d_lit, lean ? lit : 0u);
+          if (__any_sync(0xffffffffu, mine && !lean) && mine && !lean) // a ring boundary inside: masked bytes
+            for (uint32_t t = 0; t < lit; ++t) sts_u8(out_b + ((op + t) & OM), lds_u8(in_b + ((ls + t) & IM)));
+        }
+        // matches whose source was flushed long ago never depend on anything pending: L2 -> ring
+        const bool far = mine && offset > SB_LZ4_NEAR + 32 && sp + ml <= o.fl && d_m + ml <= SB_LZ4_RING;
+        if (__any_sync(0xffffffffu, far)) lz4_copy16_gs(dst + sp, out_b + d_m, far ? ml : 0u);
         __syncwarp();
-        // matches in independent-prefix rounds: everything before the first pending match is final
+        // the others run in independent-prefix rounds: everything before the first pending match is final
+        const bool nearl = mine && !far;
+        const bool lean = nearl && offset <= SB_LZ4_NEAR && (offset >= 4 || offset >= ml) && s_m + ml <= SB_LZ4_RING &&
+                          d_m + ml <= SB_LZ4_RING;
         uint32_t f = a;
         while (f < j) {
           const uint32_t first = __shfl_sync(0xffffffffu, mpos, f);
-          const bool dep = lane > f && (mpos - offset + min(ml, offset) > first);
+          const bool dep = nearl && lane > f && (sp + min(ml, offset) > first);
           const uint32_t dmask = __ballot_sync(0xffffffffu, dep || lane >= j) & ~((2u << f) - 1u);
           const uint32_t bnd = dmask ? uint32_t(__ffs(int(dmask))) - 1u : 32u; // first lane not in this round
-          if (lane >= f && lane < bnd) {
-            const uint32_t sp = mpos - offset;
-            if (offset >= 8 || offset >= ml) {
-              if (offset <= SB_LZ4_NEAR) {
-                lz4_copy_small(out_b, mpos, ml, [&](uint32_t t) { return lds_u8(out_b + ((sp + t) & OM)); });
-              } else if (offset > SB_LZ4_NEAR + 32 && sp + ml <= o.fl) { // all of it flushed: L2
-                lz4_copy_small(out_b, mpos, ml, [&](uint32_t t) { return uint32_t(__ldcg(dst + sp + t)); });
-              } else {
-                for (uint32_t t = 0; t < ml; ++t) sts_u8(out_b + ((mpos + t) & OM), o.src_byte(sp + t, mpos));
-              }
-            } else { // short self-overlap: byte by byte
-              for (uint32_t t = 0; t < ml; ++t) sts_u8(out_b + ((mpos + t) & OM), lds_u8(out_b + ((sp + t) & OM)));
-            }
-          }
+          const bool inr = lane >= f && lane < bnd && nearl;
+          lz4_copy16_ss(out_b + s_m, out_b + d_m, inr && lean ? ml : 0u);
+          if (__any_sync(0xffffffffu, inr && !lean) && inr && !lean) // overlap < 4, ring boundary, odd distances
+            for (uint32_t t = 0; t < ml; ++t) sts_u8(out_b + ((mpos + t) & OM), o.src_byte(sp + t, mpos));
           __syncwarp();
           f = min(bnd, j);
         }
