@@ -45,13 +45,32 @@ def oracle():
     return sbo
 
 
-def build_workload(rows, seed):
-    """Generate config 2 and encode it page by page (setup, untimed)."""
-    from concurrent.futures import ThreadPoolExecutor
+def build_workload(rows, seed, ctx=None):
+    """Generate config 2 and encode it page by page (setup, untimed for the decode metric).
 
+    With a Context the pages are written by THIS library's GPU encoder (sb_encode_columns:
+    stats -> choose_compressor -> codec, the product path; its device time is reported as the
+    `encode` object of the JSON line).  Without one (the --impl reference / cpu_baseline legs,
+    which may run where no GPU is visible) the oracle writer is used -- the same chooser, LZ4
+    blocks from liblz4."""
     from strawboat_b200 import workloads as wl
-    sbo = oracle()
     cols = wl.config2(rows, seed)
+    if ctx is not None:
+        import strawboat_b200 as sb
+        wo = sb.write_options(sb.C_LZ4, 2.0, PAGE_ROWS, seed=seed)
+        arrays = [sb.LeafArray(t, v, validity=val) for (_, t, v, val) in cols]
+        enc = ctx.encode_columns(arrays, wo)
+        st = ctx.last_stats()
+        out = []
+        for (name, t, v, val), e in zip(cols, enc):
+            out.append({"name": name, "type": t, "nullable": val is not None, "data": np.frombuffer(e.data, dtype=np.uint8),
+                        "metas": e.metas, "values": v, "validity": val, "pages": None, "codecs": {}})
+        enc_stats = {"device_ms": st["device_ms"], "bytes_in": int(sum(np.asarray(c[2]).nbytes for c in cols)),
+                     "bytes_out": int(sum(len(e.data) for e in enc)), "codec_pages": st["codec_pages"]}
+        return out, enc_stats
+
+    from concurrent.futures import ThreadPoolExecutor
+    sbo = oracle()
 
     def enc(c):
         name, t, v, val = c
@@ -69,7 +88,18 @@ def build_workload(rows, seed):
                 "metas": metas, "values": v, "validity": val, "pages": pages, "codecs": trees}
 
     with ThreadPoolExecutor(8) as ex:
-        return list(ex.map(enc, cols))
+        return list(ex.map(enc, cols)), None
+
+
+def split_pages_of(c):
+    """page byte strings of one encoded column (for the CPU legs)"""
+    if c["pages"] is None:
+        buf, pos, pages = c["data"].tobytes(), 0, []
+        for ln, _ in c["metas"]:
+            pages.append(buf[pos:pos + ln])
+            pos += ln
+        c["pages"] = pages
+    return c["pages"]
 
 
 class ClockSampler(threading.Thread):
@@ -109,7 +139,8 @@ def cpu_decode_time(sbo, cols, rows_limit, threads):
     jobs = []
     out_bytes = 0
     for c in cols:
-        pages = [(c["pages"][i], c["metas"][i][1]) for i in range(min(npages, len(c["pages"])))]
+        cp = split_pages_of(c)
+        pages = [(cp[i], c["metas"][i][1]) for i in range(min(npages, len(cp)))]
         jobs.append((sbo.make_leaf(c["type"], c["nullable"]), pages))
         out_bytes += sum(p[1] for p in pages) * sbo.WIDTH[c["type"]]
     best = None
@@ -132,6 +163,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-columns", action="store_true", help="skip the per-column diagnostic table")
+    ap.add_argument("--pages", default="ours", choices=["ours", "oracle"],
+                    help="who writes the input pages: this library's GPU encoder (default) or the oracle writer (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -153,7 +186,7 @@ def main():
             return
         sbo = oracle()
         sample_rows = min(rows, 2_000_000)
-        cols = build_workload(sample_rows, 42)
+        cols, _ = build_workload(sample_rows, 42)
         threads = os.cpu_count() or 1
         t_all = []
         for i in range(args.warmup + args.steps):
@@ -180,10 +213,13 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     t0 = time.time()
-    cols = build_workload(rows, 42 + rank)
-    log(f"[rank {rank}] workload built in {time.time() - t0:.1f}s:",
-        {c['name']: (len(c['data']), c['codecs']) for c in cols})
     ctx = sb.Context(local_rank, stream=torch.cuda.current_stream())
+    if args.pages == "oracle":  # diagnostic: liblz4-written LZ4 blocks
+        cols, enc_stats = build_workload(rows, 42 + rank)
+    else:
+        cols, enc_stats = build_workload(rows, 42 + rank, ctx)
+    log(f"[rank {rank}] workload built in {time.time() - t0:.1f}s:",
+        {c['name']: (len(c['data']), c['codecs']) for c in cols}, enc_stats)
     dev_cols, host_cols, keep = [], [], []
     bytes_in = 0
     for c in cols:
@@ -287,7 +323,7 @@ def main():
                 out[0]._group.release()
                 best = stc["device_ms"] if best is None else min(best, stc["device_ms"])
             ob = rows * np.dtype(sb.NP_OF[c["type"]]).itemsize
-            per_column.append({"column": c["name"], "codecs": "/".join(sorted(c["codecs"], key=lambda k: -c["codecs"][k])[:2]),
+            per_column.append({"column": c["name"], "codec_pages": stc["codec_pages"],
                                "bytes_in": int(len(c["data"])), "bytes_out": int(ob), "device_us": round(best * 1e3, 1),
                                "decoded_gbs": round(ob / best / 1e6, 1), "algorithmic_gbs": round((len(c["data"]) + ob) / best / 1e6, 1)})
 
@@ -327,6 +363,11 @@ def main():
                     host_ms_per_step=host_ms / args.steps)
         if per_column:
             line["per_column"] = per_column
+        if enc_stats:
+            line["encode"] = {"value": enc_stats["bytes_in"] / (enc_stats["device_ms"] * 1e-3) / 1e9, "unit": "GB/s (Arrow bytes in / device time)",
+                              "device_ms": enc_stats["device_ms"], "bytes_in": enc_stats["bytes_in"], "bytes_out": enc_stats["bytes_out"],
+                              "note": "sb_encode_columns wrote the pages this run decodes (one call, untimed for the decode metric)"}
+        line["config"]["pages_written_by"] = "strawboat_b200 GPU encoder" if enc_stats else "oracle writer (liblz4)"
         if e2e_ms is not None:
             line["e2e"] = {"value": world * bytes_out / (e2e_max * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_max,
                            "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out, "pinned_copy_probe": link}

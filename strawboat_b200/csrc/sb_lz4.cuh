@@ -746,7 +746,7 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
         const uint32_t j = a + (~rest ? uint32_t(__ffs(int(~rest))) - 1u : 32u - a);
         const bool mine = lane >= a && lane < j;
         const uint32_t sp = mpos - offset;
-        const uint32_t d_lit = op & OM, s_lit = ls & IM, d_m = mpos & OM, s_m = sp & OM;
+        const uint32_t d_lit = op & OM, s_lit = ls & IM, d_m = mpos & OM;
         // literals of the whole run at once
         {
           const bool lean = mine && s_lit + lit <= SB_LZ4_INR && d_lit + lit <= SB_LZ4_RING;
@@ -754,24 +754,45 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
           if (__any_sync(0xffffffffu, mine && !lean) && mine && !lean) // a ring boundary inside: masked bytes
             for (uint32_t t = 0; t < lit; ++t) sts_u8(out_b + ((op + t) & OM), lds_u8(in_b + ((ls + t) & IM)));
         }
+        // Chains: fixed-width values make a match read the output of the previous match (offset ==
+        // value width).  A match whose source lies entirely inside the destination of an earlier
+        // match of this run reads that match's own source instead (pointer jumping, distances
+        // 1,2,4,..: a chain of any length inside the run collapses in 5 steps), so the copies
+        // below stay parallel.  Only exact containment in a non-overlapping match is redirected.
+        uint32_t src = sp;
+        {
+          const uint32_t run_first = __shfl_sync(0xffffffffu, mpos, a);
+          if (__any_sync(0xffffffffu, mine && lane > a && sp + min(ml, offset) > run_first)) {
+            const bool plain = mine && offset >= ml;
+#pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) {
+              const uint32_t k_mpos = __shfl_up_sync(0xffffffffu, mpos, d), k_ml = __shfl_up_sync(0xffffffffu, ml, d);
+              const uint32_t k_src = __shfl_up_sync(0xffffffffu, src, d);
+              const bool k_plain = __shfl_up_sync(0xffffffffu, int(plain), d) != 0;
+              if (mine && lane >= a + d && k_plain && src >= k_mpos && src + ml <= k_mpos + k_ml) src = k_src + (src - k_mpos);
+            }
+          }
+        }
+        const uint32_t off2 = mpos - src; // distance to the (possibly redirected) source
+        const uint32_t s_m2 = src & OM;
         // matches whose source was flushed long ago never depend on anything pending: L2 -> ring
-        const bool far = mine && offset > SB_LZ4_NEAR + 32 && sp + ml <= o.fl && d_m + ml <= SB_LZ4_RING;
-        if (__any_sync(0xffffffffu, far)) lz4_copy16_gs(dst + sp, out_b + d_m, far ? ml : 0u);
+        const bool far = mine && off2 > SB_LZ4_NEAR + 32 && src + ml <= o.fl && d_m + ml <= SB_LZ4_RING;
+        if (__any_sync(0xffffffffu, far)) lz4_copy16_gs(dst + src, out_b + d_m, far ? ml : 0u);
         __syncwarp();
         // the others run in independent-prefix rounds: everything before the first pending match is final
         const bool nearl = mine && !far;
-        const bool lean = nearl && offset <= SB_LZ4_NEAR && (offset >= 4 || offset >= ml) && s_m + ml <= SB_LZ4_RING &&
+        const bool lean = nearl && off2 <= SB_LZ4_NEAR && (off2 >= 4 || off2 >= ml) && s_m2 + ml <= SB_LZ4_RING &&
                           d_m + ml <= SB_LZ4_RING;
         uint32_t f = a;
         while (f < j) {
           const uint32_t first = __shfl_sync(0xffffffffu, mpos, f);
-          const bool dep = nearl && lane > f && (sp + min(ml, offset) > first);
+          const bool dep = nearl && lane > f && (src + min(ml, off2) > first);
           const uint32_t dmask = __ballot_sync(0xffffffffu, dep || lane >= j) & ~((2u << f) - 1u);
           const uint32_t bnd = dmask ? uint32_t(__ffs(int(dmask))) - 1u : 32u; // first lane not in this round
           const bool inr = lane >= f && lane < bnd && nearl;
-          lz4_copy16_ss(out_b + s_m, out_b + d_m, inr && lean ? ml : 0u);
+          lz4_copy16_ss(out_b + s_m2, out_b + d_m, inr && lean ? ml : 0u);
           if (__any_sync(0xffffffffu, inr && !lean) && inr && !lean) // overlap < 4, ring boundary, odd distances
-            for (uint32_t t = 0; t < ml; ++t) sts_u8(out_b + ((mpos + t) & OM), o.src_byte(sp + t, mpos));
+            for (uint32_t t = 0; t < ml; ++t) sts_u8(out_b + ((mpos + t) & OM), o.src_byte(src + t, mpos));
           __syncwarp();
           f = min(bnd, j);
         }

@@ -137,3 +137,20 @@ def test_lz4_corrupt_streams(ctx):
         assert res.page_status[1] == 0
         # the second page is untouched by whatever happened to the first
         assert np.array_equal(res.values[8192:].view(np.uint8), good.values[8192:].view(np.uint8))
+
+
+def test_lz4_own_encoder_chains(ctx):
+    """blocks written by this library's LZ4 encoder: its greedy matcher links every match to the
+    previous value (offset == value width), the chain case of the mover (pointer jumping)."""
+    rng = np.random.default_rng(10)
+    wo = sb.write_options(sb.C_LZ4, None, 8192)
+    for type_, v in ((sbo.F64, rng.integers(0, 65536, 50_000).astype(np.float64)),
+                     (sbo.I64, rng.integers(0, 1 << 20, 50_000).astype(np.int64)),
+                     (sbo.I32, np.cumsum(rng.integers(0, 4, 70_001)).astype(np.int32)),
+                     (sbo.I16, rng.integers(0, 300, 33_333).astype(np.int16)),
+                     (sbo.F32, rng.integers(0, 1000, 20_000).astype(np.float32))):
+        enc = ctx.encode_columns([sb.LeafArray(type_, v)], wo)[0]
+        ref = oracle_decode_column(type_, False, enc.data, enc.metas)  # liblz4 reads our blocks
+        assert np.array_equal(ref["values"].view(np.uint8), v.view(np.uint8))
+        dec = ctx.batch_read_array(sb.Column(type_, False, enc.data, enc.metas))
+        assert_same(dec, ref, type_, False)

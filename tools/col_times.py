@@ -9,7 +9,7 @@ import strawboat_b200 as sb
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 only = sys.argv[2].split(',') if len(sys.argv) > 2 else None
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-cols = bench.build_workload(rows, 42)
+cols, _ = bench.build_workload(rows, 42)
 ctx = sb.Context(0, stream=torch.cuda.current_stream())
 for c in cols:
     if only and not any(c['name'].startswith(o) for o in only):
