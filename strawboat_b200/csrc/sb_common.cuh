@@ -268,6 +268,16 @@ struct Arena {
     }
     return nullptr;
   }
+  // global-only allocation (buffers that other memory paths read with ld.global)
+  __device__ __forceinline__ void *alloc_global(uint64_t bytes) {
+    bytes = (bytes + 15) & ~uint64_t(15);
+    if (uint64_t(g_end - g_cur) >= bytes) {
+      void *p = g_cur;
+      g_cur += bytes;
+      return p;
+    }
+    return nullptr;
+  }
   // shared-only allocation (small hot tables)
   __device__ __forceinline__ void *alloc_shared(uint64_t bytes) {
     bytes = (bytes + 15) & ~uint64_t(15);
@@ -285,6 +295,8 @@ struct Dctx {
   int *err;          // shared: first error of the page (0 = ok)
   uint32_t *ws;      // shared: SB_NWARP+1 words of scan workspace
   int *bcast;        // shared: 4 ints for CTA-wide broadcasts
+  const uint8_t *page_s = nullptr; // first byte of the page as the decoders see it (shared when staged)
+  const uint8_t *page_g = nullptr; // the same byte in global memory (source of cp.async streams)
   __device__ __forceinline__ void flag(int code) { atomicCAS(err, 0, code); }
 };
 

@@ -49,19 +49,46 @@ template <int W, class Gen> __device__ __forceinline__ void emit(uint8_t *dst, u
   }
 }
 
-// Basic codecs (CommonCompression::decompress, basic.rs:62-72) into `dst`.
-__device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *src, uint32_t clen, uint8_t *dst,
-                                          uint64_t out_bytes) {
-  if (codec == SB_C_NONE) {
-    if (uint64_t(clen) != out_bytes) { // copy_from_slice length mismatch panics (basic.rs:68)
-      cx.flag(SB_PANIC);
-      return false;
+// LZ4 value block into `dst` (one instance for every caller: the scanner / mover code is large).
+__device__ __noinline__ bool dec_lz4_block(Dctx &cx, const uint8_t *src, uint32_t clen, uint8_t *dst, uint64_t out_bytes) {
+    // Nested LZ4 blocks (Dict indices, Freq exceptions, boolean / binary buffers).  Blocks of
+    // some size run on the scanner / mover pair of sb_lz4.cuh (warps 0 and 1 of this CTA; the
+    // rings come out of the shared arena, the stream is read from the page's global copy, the
+    // output must be global because the mover re-reads far match sources with ld.global).
+    Arena mark = cx.ar;
+    Lz4Shared *sh = nullptr;
+    uint8_t *gdst = nullptr;
+    if (clen >= 96 && out_bytes <= SB_LZ4_MAXPOS / 2 && cx.page_g != nullptr) {
+      gdst = __isGlobal(dst) ? dst : static_cast<uint8_t *>(cx.ar.alloc_global(out_bytes + 16));
+      if (gdst) sh = static_cast<Lz4Shared *>(cx.ar.alloc_shared(sizeof(Lz4Shared)));
     }
-    copy_bytes(dst, src, out_bytes);
-    return true;
-  }
-  if (codec == SB_C_LZ4) {
     __syncthreads();
+    if (sh) {
+      if (threadIdx.x == 0) {
+        sh->produced = sh->in_ready = sh->consumed = sh->m_q = sh->abort = 0;
+        cx.bcast[0] = 0;
+      }
+      __syncthreads();
+      const uint8_t *gsrc = cx.page_g + (src - cx.page_s);
+      int rc = 0;
+      if (threadIdx.x < 32) rc = lz4_scan(gsrc, clen, sh);
+      else if (threadIdx.x < 64) rc = lz4_move(gdst, uint32_t(out_bytes), uint32_t(uintptr_t(gsrc) & 15) + clen, sh);
+      if (rc) cx.bcast[0] = rc;
+      __syncthreads();
+      rc = cx.bcast[0];
+      if (rc == 0 && gdst != dst) {
+        __threadfence_block();
+        copy_bytes(dst, gdst, out_bytes);
+      }
+      cx.ar = mark;
+      __syncthreads();
+      if (rc) {
+        cx.flag(rc);
+        return false;
+      }
+      return true;
+    }
+    cx.ar = mark;
     if (threadIdx.x < 32) {
       FlatOut fo{dst};
       int rc = lz4_decode_warp2(src, clen, fo, uint32_t(out_bytes));
@@ -74,7 +101,20 @@ __device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *sr
       return false;
     }
     return true;
+}
+
+// Basic codecs (CommonCompression::decompress, basic.rs:62-72) into `dst`.
+__device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *src, uint32_t clen, uint8_t *dst,
+                                          uint64_t out_bytes) {
+  if (codec == SB_C_NONE) {
+    if (uint64_t(clen) != out_bytes) { // copy_from_slice length mismatch panics (basic.rs:68)
+      cx.flag(SB_PANIC);
+      return false;
+    }
+    copy_bytes(dst, src, out_bytes);
+    return true;
   }
+  if (codec == SB_C_LZ4) return dec_lz4_block(cx, src, clen, dst, out_bytes);
   cx.flag(SB_NYI); // zstd / snappy pages: SURVEY §8 f3
   return false;
 }

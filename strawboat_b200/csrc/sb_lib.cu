@@ -70,31 +70,34 @@ __device__ __forceinline__ bool lz4_side_page(const uint8_t *p, uint32_t len, bo
 // incompressible data) -> plain copy in the main kernel.
 // Jobs are binned by compressed size: long streams from the front of `jobs`, short ones from
 // the back, so the (latency-bound) long pages start first and the short ones fill the tail.
-__device__ __forceinline__ bool lz4_stored_block(const uint8_t *s, uint32_t clen, uint32_t dlen, uint32_t *lit_start) {
+// One WARP per page (the length bytes of a stored block are checked 32 at a time).
+__device__ __forceinline__ bool lz4_stored_block(const uint8_t *s, uint32_t clen, uint32_t dlen) {
+  const uint32_t lane = threadIdx.x & 31;
   if (dlen < 15 || clen < 2 || s[0] != 0xF0) return false;
   uint32_t ne = (dlen - 15) / 255 + 1; // length-extension bytes: (ne-1) x 255, then the rest
-  if (ne > 2048 || uint64_t(clen) != 1ull + ne + dlen) return false;
+  if (ne > 4096 || uint64_t(clen) != 1ull + ne + dlen) return false;
   bool ok = s[ne] == (dlen - 15) % 255;
-  for (uint32_t i = 1; i < ne; ++i) ok &= s[i] == 255;
-  *lit_start = 1 + ne;
-  return ok;
+  for (uint32_t i = 1 + lane; i < ne; i += 32) ok &= s[i] == 255;
+  return __all_sync(0xffffffffu, ok);
 }
 
 __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, uint32_t n_pages,
                                    Lz4Job *jobs, uint32_t *n_jobs, uint8_t *side_flags) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_pages) return;
   const PageDesc pg = pages[i];
   const ColDesc col = cols[pg.col];
   if (!is_fixed_type(col.type) || col.n_nested > 1) return;
   uint32_t vb, clen;
   if (!lz4_side_page(pg.src, pg.len, col.nullable != 0, &vb, &clen)) return;
-  const uint32_t dlen = pg.num_values * uint32_t(col.W);
-  uint32_t lit_start;
-  if (lz4_stored_block(pg.src + vb + 9, clen, dlen, &lit_start)) {
-    side_flags[i] = 2;
+  const uint64_t dlen64 = uint64_t(pg.num_values) * uint32_t(col.W);
+  if (dlen64 > SB_LZ4_MAXPOS / 2 || clen > SB_LZ4_MAXPOS / 2) return; // positions are 30-bit in sb_lz4_kernel
+  const uint32_t dlen = uint32_t(dlen64);
+  if (lz4_stored_block(pg.src + vb + 9, clen, dlen)) {
+    if (lane == 0) side_flags[i] = 2;
     return;
   }
+  if (lane != 0) return;
   Lz4Job j;
   j.src = pg.src + vb + 9;
   j.dst = col.values + pg.out_elem * uint64_t(col.W);
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(64, 16)
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ bool is_binary_type(int t) { return t == SB_BINARY || t == SB_LARGE_BINARY; }
 
-__global__ void __launch_bounds__(SB_NT)
+__global__ void __launch_bounds__(SB_NT, 4)
     sb_decode_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols,
                      const WorkItem *__restrict__ items, uint32_t n_items, uint32_t *counter, uint8_t *scratch,
                      uint64_t scratch_per_cta, int32_t *status, uint32_t stage_cap, uint32_t smem_bytes,
@@ -220,6 +223,8 @@ __global__ void __launch_bounds__(SB_NT)
       cx.ar.s_cur = dsm;
     }
 
+    cx.page_s = p;
+    cx.page_g = pg.src;
     const uint32_t avail = pg.len;
     uint32_t n = pg.num_values;
     bool ok = true;
@@ -723,7 +728,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   if (n_items) {
     if (any_fixed) {
       // D0: find top-level LZ4 blocks; run them warp-per-page next to the main kernel
-      sb_classify_kernel<<<uint32_t((n_pages_total + 255) / 256), 256, 0, st>>>(d_pages, d_cols, uint32_t(n_pages_total), d_jobs,
+      sb_classify_kernel<<<uint32_t((n_pages_total + 7) / 8), 256, 0, st>>>(d_pages, d_cols, uint32_t(n_pages_total), d_jobs,
                                                                               d_counters + 2, d_flags);
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_fork, st));
       SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
