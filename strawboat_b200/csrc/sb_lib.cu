@@ -330,6 +330,19 @@ extern "C" {
 
 const char *sb_version(void) { return "strawboat_b200 0.1 (sm_100a)"; }
 
+#ifdef SB_LZ4_PROF
+// diagnostic build only (make PROF=1): cumulative cycles per mover phase, see tools/lz4_prof.py
+int32_t sb_debug_lz4_prof(unsigned long long *out32, int32_t reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out32, sb::g_lz4_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return SB_CUDA;
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(sb::g_lz4_prof, z, sizeof(z));
+  }
+  return SB_OK;
+}
+#endif
+
 int32_t sb_ctx_create(int32_t device, sb_ctx **out) {
   if (!out) return SB_INVALID_ARG;
   *out = nullptr;

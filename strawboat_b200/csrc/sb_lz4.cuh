@@ -200,6 +200,15 @@ __device__ __forceinline__ void sts_vol(uint32_t a, uint32_t v) {
 }
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
+#ifdef SB_LZ4_PROF
+__device__ unsigned long long g_lz4_prof[32];
+#define LZ4_T(var) const uint32_t var = clock()
+#define LZ4_ACC(slot, t0, t1) prof[slot] += (t1) - (t0)
+#else
+#define LZ4_T(var)
+#define LZ4_ACC(slot, t0, t1)
+#endif
+
 struct __align__(16) Lz4Shared {
   uint8_t out[SB_LZ4_RING];
   uint8_t in[SB_LZ4_INR];
@@ -318,9 +327,10 @@ __device__ int lz4_scan(const uint8_t *src, uint32_t clen, Lz4Shared *sh) {
         s.ready = s.issued;
       }
       s.own = q;
+      // publish BEFORE requesting new chunks: the release fence then has no copies in flight to wait for
+      if (s.seq - s.pub >= 32 || s.ready != s.ready_pub) s.publish();
       s.refresh();
       s.issue_allowed();
-      if (s.seq - s.pub >= 32 || s.ready != s.ready_pub) s.publish();
       if (!s.room(12) || !s.need(min(end, q + 64))) {
         rc = -1; // aborted by the mover (it reports the status)
         break;
@@ -532,13 +542,58 @@ template <int K> __device__ __forceinline__ void lz4_copy4_gs(const uint8_t *s, 
       "r"(d), "r"(n), "n"(K), "n"(K + 1), "n"(K + 2), "n"(K + 3)
       : "memory");
 }
+// Bytes [K, K+8) of a short run: 8 loads in flight before the first store (one shared-memory
+// latency per 8 bytes); predicates are recomputed for the stores (only 7 predicate registers).
+template <int K> __device__ __forceinline__ void lz4_copy8_ss(uint32_t s, uint32_t d, uint32_t n) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p<4>;\n\t"
+      ".reg .u32 v<8>;\n\t"
+      "setp.gt.u32 p0, %2, %3;\n\t"
+      "setp.gt.u32 p1, %2, %4;\n\t"
+      "setp.gt.u32 p2, %2, %5;\n\t"
+      "setp.gt.u32 p3, %2, %6;\n\t"
+      "@p0 ld.shared.u8 v0, [%0+%3];\n\t"
+      "@p1 ld.shared.u8 v1, [%0+%4];\n\t"
+      "@p2 ld.shared.u8 v2, [%0+%5];\n\t"
+      "@p3 ld.shared.u8 v3, [%0+%6];\n\t"
+      "setp.gt.u32 p0, %2, %7;\n\t"
+      "setp.gt.u32 p1, %2, %8;\n\t"
+      "setp.gt.u32 p2, %2, %9;\n\t"
+      "setp.gt.u32 p3, %2, %10;\n\t"
+      "@p0 ld.shared.u8 v4, [%0+%7];\n\t"
+      "@p1 ld.shared.u8 v5, [%0+%8];\n\t"
+      "@p2 ld.shared.u8 v6, [%0+%9];\n\t"
+      "@p3 ld.shared.u8 v7, [%0+%10];\n\t"
+      "@p0 st.shared.u8 [%1+%7], v4;\n\t"
+      "@p1 st.shared.u8 [%1+%8], v5;\n\t"
+      "@p2 st.shared.u8 [%1+%9], v6;\n\t"
+      "@p3 st.shared.u8 [%1+%10], v7;\n\t"
+      "setp.gt.u32 p0, %2, %3;\n\t"
+      "setp.gt.u32 p1, %2, %4;\n\t"
+      "setp.gt.u32 p2, %2, %5;\n\t"
+      "setp.gt.u32 p3, %2, %6;\n\t"
+      "@p0 st.shared.u8 [%1+%3], v0;\n\t"
+      "@p1 st.shared.u8 [%1+%4], v1;\n\t"
+      "@p2 st.shared.u8 [%1+%5], v2;\n\t"
+      "@p3 st.shared.u8 [%1+%6], v3;\n\t"
+      "}" ::"r"(s),
+      "r"(d), "r"(n), "n"(K), "n"(K + 1), "n"(K + 2), "n"(K + 3), "n"(K + 4), "n"(K + 5), "n"(K + 6), "n"(K + 7)
+      : "memory");
+}
 // n <= 16 bytes per lane (n = 0 for lanes that do not take part); whole-warp call: the upper
-// groups are skipped when no lane needs them
-__device__ __forceinline__ void lz4_copy16_ss(uint32_t s, uint32_t d, uint32_t n) {
+// groups are skipped when no lane needs them (`gt4` / `gt8`: warp-uniform "some lane has n > 4 / 8")
+// `wide`: sources are at least 8 bytes away from their destinations (or in another buffer)
+__device__ __forceinline__ void lz4_copy16_ss(uint32_t s, uint32_t d, uint32_t n, bool gt4, bool gt8, bool wide) {
+  if (wide && gt4) {
+    lz4_copy8_ss<0>(s, d, n);
+    if (gt8) lz4_copy8_ss<8>(s, d, n);
+    return;
+  }
   lz4_copy4_ss<0>(s, d, n);
-  if (__any_sync(0xffffffffu, n > 4)) {
+  if (gt4) {
     lz4_copy4_ss<4>(s, d, n);
-    if (__any_sync(0xffffffffu, n > 8)) {
+    if (gt8) {
       lz4_copy4_ss<8>(s, d, n);
       lz4_copy4_ss<12>(s, d, n);
     }
@@ -567,17 +622,29 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
   const uint32_t out_b = o.out_b;
   uint32_t cons = 0, op_base = 0;
   int rc = 0;
+#ifdef SB_LZ4_PROF
+  uint32_t prof[12] = {0};
+  struct ProfDump {
+    uint32_t *p;
+    __device__ ~ProfDump() {
+      if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 12; ++i) atomicAdd(&g_lz4_prof[i], (unsigned long long)p[i]);
+    }
+  } prof_dump{prof};
+#endif
   auto wait_in = [&](uint32_t upto) -> bool { // stream bytes [.., upto) in the ring
     for (;;) {
       if (lds_vol(sh_b + offsetof(Lz4Shared, in_ready)) >= upto) break;
       if (lds_vol(sh_b + offsetof(Lz4Shared, abort))) return false;
       __nanosleep(64);
     }
-    fence_cta();
     return true;
   };
+  // No fences on the mover side: its reads of the rings and its publications are shared-memory
+  // accesses of ONE warp, which the LSU performs in program order; a MEMBAR here would also wait
+  // for the write-behind global stores in flight (~1 us), on the critical path of every batch.
   auto release_in = [&](uint32_t q) {
-    fence_cta();
+    __syncwarp();
     if (lane == 0) sts_vol(sh_b + offsetof(Lz4Shared, m_q), q);
   };
   // whole-warp literal copy of stream bytes [ls, ls+lit) to output position op, streaming
@@ -613,17 +680,23 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
     return 0;
   };
   for (;;) {
+    LZ4_T(t0);
     uint32_t prod;
     while ((prod = lds_vol(sh_b + offsetof(Lz4Shared, produced))) == cons) {
       if (lds_vol(sh_b + offsetof(Lz4Shared, abort))) return 0; // the scanner reports
       __nanosleep(32);
     }
-    fence_cta();
     const uint32_t nb = min(prod - cons, 32u);
+    LZ4_T(t1);
+    LZ4_ACC(0, t0, t1);
+#ifdef SB_LZ4_PROF
+    prof[10] += 1;
+    prof[11] += nb;
+#endif
     // ---- one sequence per lane: parse
     uint32_t q = 0, kind = LZ4_E_SEQ, lit = 0, ml = 0, offset = 1, ls = 0, qn = 0;
     if (lane < nb) {
-      const uint32_t e = sh->q[(cons + lane) & (SB_LZ4_Q - 1)];
+      const uint32_t e = lds_vol(sh_b + offsetof(Lz4Shared, q) + (((cons + lane) & (SB_LZ4_Q - 1)) << 2));
       q = e & SB_LZ4_MAXPOS;
       kind = e >> 30;
       const uint32_t tok = lds_u8(in_b + (q & IM));
@@ -655,6 +728,8 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
       qn = kind == LZ4_E_SEQ ? r : q;
     }
     const uint32_t spec_mask = __ballot_sync(0xffffffffu, lane < nb && kind != LZ4_E_SEQ);
+    LZ4_T(t2);
+    LZ4_ACC(1, t1, t2);
     uint32_t i = 0;
     while (i < nb) {
       const uint32_t spec = spec_mask >> i;
@@ -717,6 +792,7 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
         continue;
       }
       // ---- segment [i, e) of ordinary sequences: output positions by a warp scan
+      LZ4_T(t3);
       const bool in_seg = lane >= i && lane < e;
       const uint32_t len = in_seg ? lit + ml : 0u;
       const uint32_t incl = warp_incl_scan(len);
@@ -729,6 +805,8 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
         break;
       }
       const uint32_t small_mask = __ballot_sync(0xffffffffu, in_seg && lit <= SB_LZ4_SMALL && ml <= SB_LZ4_SMALL);
+      LZ4_T(t4);
+      LZ4_ACC(2, t3, t4);
       uint32_t a = i;
       while (a < e) {
         if (!(small_mask & (1u << a))) {
@@ -742,6 +820,7 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
           continue;
         }
         // run [a, j) of short sequences, one per lane
+        LZ4_T(t5);
         const uint32_t rest = small_mask >> a;
         const uint32_t j = a + (~rest ? uint32_t(__ffs(int(~rest))) - 1u : 32u - a);
         const bool mine = lane >= a && lane < j;
@@ -750,10 +829,13 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
         // literals of the whole run at once
         {
           const bool lean = mine && s_lit + lit <= SB_LZ4_INR && d_lit + lit <= SB_LZ4_RING;
-          lz4_copy16_ss(in_b + s_lit, out_b + d_lit, lean ? lit : 0u);
+          lz4_copy16_ss(in_b + s_lit, out_b + d_lit, lean ? lit : 0u, __any_sync(0xffffffffu, mine && lit > 4),
+                        __any_sync(0xffffffffu, mine && lit > 8), true);
           if (__any_sync(0xffffffffu, mine && !lean) && mine && !lean) // a ring boundary inside: masked bytes
             for (uint32_t t = 0; t < lit; ++t) sts_u8(out_b + ((op + t) & OM), lds_u8(in_b + ((ls + t) & IM)));
         }
+        LZ4_T(t6);
+        LZ4_ACC(3, t5, t6);
         // Chains: fixed-width values make a match read the output of the previous match (offset ==
         // value width).  A match whose source lies entirely inside the destination of an earlier
         // match of this run reads that match's own source instead (pointer jumping, distances
@@ -773,6 +855,8 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
             }
           }
         }
+        LZ4_T(t7);
+        LZ4_ACC(4, t6, t7);
         const uint32_t off2 = mpos - src; // distance to the (possibly redirected) source
         const uint32_t s_m2 = src & OM;
         // matches whose source was flushed long ago never depend on anything pending: L2 -> ring
@@ -780,37 +864,65 @@ __device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Sha
         if (__any_sync(0xffffffffu, far)) lz4_copy16_gs(dst + src, out_b + d_m, far ? ml : 0u);
         __syncwarp();
         // the others run in independent-prefix rounds: everything before the first pending match is final
+        LZ4_T(t8);
+        LZ4_ACC(5, t7, t8);
         const bool nearl = mine && !far;
         const bool lean = nearl && off2 <= SB_LZ4_NEAR && (off2 >= 4 || off2 >= ml) && s_m2 + ml <= SB_LZ4_RING &&
                           d_m + ml <= SB_LZ4_RING;
+        const bool gt4 = __any_sync(0xffffffffu, nearl && ml > 4), gt8 = __any_sync(0xffffffffu, nearl && ml > 8);
+        const bool any_slow = __any_sync(0xffffffffu, nearl && !lean);
+        const bool wide = !__any_sync(0xffffffffu, lean && off2 < 8 && off2 < ml);
+        // K = last lane whose (pending) match this lane may read: mpos is increasing, so it is the
+        // number of run lanes with mpos < source end, found by a 5-step binary search over the warp.
+        // A lane can go as soon as the round starts beyond K.
+        uint32_t K = 0;
+        {
+          const uint32_t s_end = src + min(ml, off2);
+          uint32_t lo = a, hi = lane; // invariant: mpos[lo..] candidates; count lanes in [a, lane) with mpos < s_end
+#pragma unroll
+          for (int it = 0; it < 5; ++it) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t m_mid = __shfl_sync(0xffffffffu, mpos, mid & 31);
+            if (lo < hi) {
+              if (m_mid < s_end) lo = mid + 1;
+              else hi = mid;
+            }
+          }
+          K = lo; // lanes [a, lo) have mpos < s_end: this lane waits until the round start f >= lo
+        }
         uint32_t f = a;
         while (f < j) {
-          const uint32_t first = __shfl_sync(0xffffffffu, mpos, f);
-          const bool dep = nearl && lane > f && (src + min(ml, off2) > first);
-          const uint32_t dmask = __ballot_sync(0xffffffffu, dep || lane >= j) & ~((2u << f) - 1u);
+          const bool blocked = nearl && lane > f && K > f;
+          const uint32_t dmask = __ballot_sync(0xffffffffu, blocked || lane >= j) & ~((2u << f) - 1u);
           const uint32_t bnd = dmask ? uint32_t(__ffs(int(dmask))) - 1u : 32u; // first lane not in this round
           const bool inr = lane >= f && lane < bnd && nearl;
-          lz4_copy16_ss(out_b + s_m2, out_b + d_m, inr && lean ? ml : 0u);
-          if (__any_sync(0xffffffffu, inr && !lean) && inr && !lean) // overlap < 4, ring boundary, odd distances
+          lz4_copy16_ss(out_b + s_m2, out_b + d_m, inr && lean ? ml : 0u, gt4, gt8, wide);
+          if (any_slow && inr && !lean) // overlap < 4, ring boundary, odd distances
             for (uint32_t t = 0; t < ml; ++t) sts_u8(out_b + ((mpos + t) & OM), o.src_byte(src + t, mpos));
           __syncwarp();
           f = min(bnd, j);
         }
+        LZ4_T(t9);
+        LZ4_ACC(6, t8, t9);
         const uint32_t op_end = __shfl_sync(0xffffffffu, mpos + ml, j - 1);
         if (op_end - o.fl >= SB_LZ4_FLUSHQ) o.flush_to(op_end, false);
+        LZ4_T(t10);
+        LZ4_ACC(7, t9, t10);
         a = j;
       }
       op_base += seg_total;
       i = e;
     }
     if (rc) break;
+    LZ4_T(t11);
     cons += nb;
     const uint32_t q_next = __shfl_sync(0xffffffffu, qn, nb - 1);
-    fence_cta();
     if (lane == 0) {
       sts_vol(sh_b + offsetof(Lz4Shared, m_q), q_next);
       sts_vol(sh_b + offsetof(Lz4Shared, consumed), cons);
     }
+    LZ4_T(t12);
+    LZ4_ACC(8, t11, t12);
   }
   if (lane == 0) sts_vol(sh_b + offsetof(Lz4Shared, abort), 1u);
   return rc > 0 ? rc : 0;
