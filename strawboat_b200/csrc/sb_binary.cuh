@@ -398,9 +398,40 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
       return false;
     }
     // offsets: first page keeps raw[0..n]; later pages drop raw[0] and rebase by `last`
-    for (uint32_t j = tid + (first ? 0u : 1u); j <= n; j += SB_NT) {
-      uint64_t v = OW == 4 ? uint64_t(int64_t(int32_t(ld_u32u(raw + uint64_t(j) * 4)))) : ld_u64u(raw + uint64_t(j) * 8);
-      out_off[j] = O(base + v);
+    {
+      // 16-byte vectors: one unaligned 16-byte read of the page (two aligned loads + funnel
+      // shifts), add the rebase, one aligned 16-byte store; scalar head / tail
+      constexpr uint32_t E = 16 / OW;
+      const uint32_t j0 = first ? 0u : 1u;
+      uint32_t head = uint32_t((16 - (uintptr_t(out_off + j0) & 15)) & 15) / OW; // elements before the first aligned vector
+      const uint32_t total = n + 1 - j0;
+      head = min(head, total);
+      const uint32_t nvec = (total - head) / E;
+      auto scalar = [&](uint32_t j) {
+        uint64_t v = OW == 4 ? uint64_t(int64_t(int32_t(ld_u32u(raw + uint64_t(j) * 4)))) : ld_u64u(raw + uint64_t(j) * 8);
+        out_off[j] = O(base + v);
+      };
+      for (uint32_t j = j0 + tid; j < j0 + head; j += SB_NT) scalar(j);
+      auto rebase = [&](uint4 w) {
+        if (OW == 4) {
+          const uint32_t b32 = uint32_t(base);
+          w.x += b32, w.y += b32, w.z += b32, w.w += b32;
+        } else {
+          uint64_t a = (uint64_t(w.y) << 32 | w.x) + base, c = (uint64_t(w.w) << 32 | w.z) + base;
+          w.x = uint32_t(a), w.y = uint32_t(a >> 32), w.z = uint32_t(c), w.w = uint32_t(c >> 32);
+        }
+        return w;
+      };
+      const uint8_t *rv = raw + uint64_t(j0 + head) * OW;
+      uint4 *ov = reinterpret_cast<uint4 *>(out_off + j0 + head);
+      uint32_t v = tid;
+      for (; v + 3 * SB_NT < nvec; v += 4 * SB_NT) { // four vectors in flight per thread
+        uint4 a = ld_u128u(rv + (uint64_t(v) << 4)), b = ld_u128u(rv + (uint64_t(v + SB_NT) << 4));
+        uint4 c = ld_u128u(rv + (uint64_t(v + 2 * SB_NT) << 4)), e = ld_u128u(rv + (uint64_t(v + 3 * SB_NT) << 4));
+        ov[v] = rebase(a), ov[v + SB_NT] = rebase(b), ov[v + 2 * SB_NT] = rebase(c), ov[v + 3 * SB_NT] = rebase(e);
+      }
+      for (; v < nvec; v += SB_NT) ov[v] = rebase(ld_u128u(rv + (uint64_t(v) << 4)));
+      for (uint32_t j = j0 + head + nvec * E + tid; j <= n; j += SB_NT) scalar(j);
     }
     __syncthreads();
     cx.ar = mark;
