@@ -10,7 +10,7 @@
 
 namespace sb {
 
-struct BinEntry {
+struct __align__(8) BinEntry {
   uint32_t pos; // byte position of the entry's payload inside the page
   uint32_t len;
 };
@@ -309,25 +309,30 @@ __device__ void emit_rows(Dctx &cx, uint32_t n, RowSrc &rs, typename OffT<OW>::T
   uint64_t run = 0; // bytes emitted by previous chunks
   for (uint32_t r0 = 0; r0 < n; r0 += CH) {
     uint32_t lens[RPT], sum = 0;
+    const uint8_t *ptrs[RPT];
 #pragma unroll
-    for (uint32_t j = 0; j < RPT; ++j) {
+    for (uint32_t j = 0; j < RPT; ++j) { // one lookup per row: (payload pointer, length), all four in flight
       uint32_t r = r0 + tid * RPT + j;
-      lens[j] = r < n ? rs.len(r) : 0u;
+      lens[j] = 0;
+      ptrs[j] = nullptr;
+      if (r < n) rs.get(r, &ptrs[j], &lens[j]);
       sum += lens[j];
     }
     uint32_t total;
     uint64_t pre = run + block_excl_scan(sum, cx.ws, &total);
+    O offs[RPT];
 #pragma unroll
     for (uint32_t j = 0; j < RPT; ++j) {
-      uint32_t r = r0 + tid * RPT + j;
-      if (r < n) {
-        const uint8_t *s = rs.ptr(r);
-        uint8_t *d = out_val + pre;
-        for (uint32_t i = 0; i < lens[j]; ++i) d[i] = s[i];
-        pre += lens[j];
-        out_off[r + 1] = O(base + pre);
-      }
+      const uint8_t *s = ptrs[j];
+      uint8_t *d = out_val + pre;
+      for (uint32_t i = 0; i < lens[j]; ++i) d[i] = s[i];
+      pre += lens[j];
+      offs[j] = O(base + pre);
     }
+    const uint32_t r = r0 + tid * RPT;
+#pragma unroll
+    for (uint32_t j = 0; j < RPT; ++j)
+      if (r + j < n) out_off[r + j + 1] = offs[j];
     run += total;
   }
 }
@@ -337,13 +342,11 @@ struct RowsDict {
   const BinEntry *tab;
   const uint8_t *page;
   uint32_t k;
-  __device__ __forceinline__ uint32_t len(uint32_t r) const {
+  __device__ __forceinline__ void get(uint32_t r, const uint8_t **p, uint32_t *l) const {
     uint32_t id = idx[r];
-    return id < k ? tab[id].len : 0u;
-  }
-  __device__ __forceinline__ const uint8_t *ptr(uint32_t r) const {
-    uint32_t id = idx[r];
-    return page + (id < k ? tab[id].pos : 0u);
+    uint2 e = id < k ? *reinterpret_cast<const uint2 *>(tab + id) : make_uint2(0u, 0u); // {pos, len}
+    *p = page + e.x;
+    *l = e.y;
   }
 };
 struct RowsFreq {
@@ -352,21 +355,36 @@ struct RowsFreq {
   const uint8_t *page;
   const uint8_t *top;
   uint32_t top_len;
-  __device__ __forceinline__ uint32_t len(uint32_t r) const {
+  __device__ __forceinline__ void get(uint32_t r, const uint8_t **p, uint32_t *l) const {
     uint32_t k = rank[r];
-    return k ? tab[k - 1].len : top_len;
-  }
-  __device__ __forceinline__ const uint8_t *ptr(uint32_t r) const {
-    uint32_t k = rank[r];
-    return k ? page + tab[k - 1].pos : top;
+    if (k) {
+      uint2 e = *reinterpret_cast<const uint2 *>(tab + (k - 1));
+      *p = page + e.x;
+      *l = e.y;
+    } else {
+      *p = top;
+      *l = top_len;
+    }
   }
 };
 struct RowsConst {
   const uint8_t *val;
   uint32_t vlen;
-  __device__ __forceinline__ uint32_t len(uint32_t) const { return vlen; }
-  __device__ __forceinline__ const uint8_t *ptr(uint32_t) const { return val; }
+  __device__ __forceinline__ void get(uint32_t, const uint8_t **p, uint32_t *l) const {
+    *p = val;
+    *l = vlen;
+  }
 };
+
+// The plan pass left the (pos, len) table of the page's dictionary / exception entries in global
+// memory: copy it next to the page in shared memory when it fits (8 bytes per entry), so the
+// per-row lookups of emit_rows are shared-memory loads.  The caller synchronises.
+__device__ __forceinline__ const BinEntry *stage_entries(Dctx &cx, const BinEntry *tab, uint32_t k) {
+  BinEntry *s = static_cast<BinEntry *>(cx.ar.alloc_shared(uint64_t(k) * sizeof(BinEntry)));
+  if (!s) return tab;
+  for (uint32_t i = threadIdx.x; i < k; i += SB_NT) reinterpret_cast<uint2 *>(s)[i] = reinterpret_cast<const uint2 *>(tab)[i];
+  return s;
+}
 
 // decompress_binary (binary/mod.rs:95-183).  out_off = &offsets[out_elem]; out_val = values
 // + out_byte; `base` = out_byte (the last offset already in the column); `first` = the
@@ -478,6 +496,7 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
       return false;
     }
     uint32_t k = ld_u32u(b.body + used);
+    tab = stage_entries(cx, tab, k);
     __syncthreads();
     RowsDict rs{idx, tab, page, k};
     emit_rows<OW>(cx, n, rs, out_off, out_val, base, first);
@@ -516,6 +535,8 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
     __syncthreads();
     // exception e is the e-th VISITED exception row: ranks of rows < n are dense because
     // the bitmap is sorted, except for (malformed) rows >= n which the size pass ignored too
+    tab = stage_entries(cx, tab, n); // at most one exception per row
+    __syncthreads();
     RowsFreq rs{rank, tab, page, b.body + 8, uint32_t(top_len)};
     emit_rows<OW>(cx, n, rs, out_off, out_val, base, first);
     __syncthreads();

@@ -438,6 +438,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   // ---- host pass: validate, count pages / work items
   uint64_t n_pages_total = 0, n_items = 0, n_plan = 0, n_entries = 0, max_elems_bytes = 0;
   uint32_t max_stage = 0;
+  uint64_t max_need = 0; // staged page + a u32 index / rank buffer for its rows (Dict, Freq) + small tables
   const uint32_t stage_cap = kSmemMax - kArenaMin;
   auto col_binary = [](const sb_column_in &ci) { return ci.leaf.type == SB_BINARY || ci.leaf.type == SB_LARGE_BINARY; };
   auto col_nested = [](const sb_column_in &ci) { return ci.leaf.n_nested > 1; };
@@ -460,6 +461,9 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       if (m.length + 32 <= stage_cap) {
         n_items += 1;
         max_stage = std::max<uint32_t>(max_stage, uint32_t(m.length));
+        // a page that is much smaller than its decoded size is Dict / Freq / RLE coded: give its
+        // index buffer (4 bytes per row) room in shared memory instead of the L2 scratch
+        if (m.length < m.num_values * W) max_need = std::max<uint64_t>(max_need, m.length + 4 * m.num_values + 16 * 1024);
       } else {
         uint64_t out_bytes = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * W;
         bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type) && !col_nested(ci);
@@ -635,6 +639,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
 
   // ---- launch configuration
   uint32_t smem = uint32_t(align_up(std::min<uint64_t>(uint64_t(max_stage) + 48, stage_cap) + kArenaMin, 1024));
+  smem = std::max<uint32_t>(smem, uint32_t(std::min<uint64_t>(align_up(max_need, 1024), kSmemMax)));
   smem = std::min(std::max(smem, kSmemMin), kSmemMax);
   if (ctx->occ_smem != smem) { // occupancy queries cost tens of microseconds: once per shared-memory size
     int q = 1;
