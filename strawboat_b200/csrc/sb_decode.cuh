@@ -316,57 +316,138 @@ template <bool DELTA> __device__ bool dec_bitpack(Dctx &cx, const uint8_t *src, 
 }
 
 // ------------------------------------------------------------------------------------
-// Patas (double/patas.rs:107-132).  Serial variable-length stream; v1: one thread walks it
-// with a 128-entry ring of previous values in shared memory (reference_diff <= 127).
+// Patas (double/patas.rs:107-132): [first value] then per value
+//   [u16 = ref << 9 | (sig & 7) << 6 | tz][sig bytes of (xor >> tz)],  v[i] = (x << tz) ^ v[i - ref].
+// Two chains: where value i starts (each header tells the length of its payload) and what
+// value i is (it refers to one of the 127 values before it).
+//   1. positions: warp 0 walks the stream like the LZ4 scanner -- every lane decodes the two bytes
+//      at its window position as a header, the real chain is followed with one SHFL per value;
+//      all format checks of the reference loop (short stream, sig > W, ref == 0, ref > i) happen
+//      here, in stream order, so the first failure is the reference's failure;
+//   2. values: 128 values per step, one per thread.  References into earlier steps are final;
+//      chains inside the step are collapsed by pointer jumping on (xor accumulator, reference)
+//      pairs in shared memory, at most 7 rounds.
 // ------------------------------------------------------------------------------------
 template <int W> __device__ bool dec_patas(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, uint8_t *dst) {
   using T = typename Elem<W>::T;
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  if (n == 0) { // `length - 1` underflows (patas.rs:117)
+    cx.flag(SB_PANIC);
+    return false;
+  }
+  if (avail < uint32_t(W)) {
+    cx.flag(SB_IO);
+    return false;
+  }
   Arena mark = cx.ar;
-  uint64_t *ring = static_cast<uint64_t *>(cx.ar.alloc_shared(128 * 8));
-  if (!ring) ring = static_cast<uint64_t *>(cx.ar.alloc(128 * 8));
+  uint32_t *pos = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
+  uint64_t *hist = static_cast<uint64_t *>(cx.ar.alloc(256 * 8));            // final values, index & 255
+  uint64_t *acc_s = static_cast<uint64_t *>(cx.ar.alloc(2 * SB_NT * 8));     // double-buffered accumulators
+  uint32_t *ptr_s = static_cast<uint32_t *>(cx.ar.alloc(2 * SB_NT * 4));     // double-buffered references
+  if (!pos || !hist || !acc_s || !ptr_s) {
+    cx.flag(SB_NYI);
+    return false;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  // ---- 1. positions (warp 0)
+  if (tid < 32) {
     int rc = 0;
-    if (n == 0) rc = SB_PANIC; // `length - 1` underflows (patas.rs:117)
-    else if (avail < uint32_t(W)) rc = SB_IO;
-    else {
-      T *out = reinterpret_cast<T *>(dst);
-      T first = ld_elem_u<W>(src);
-      out[0] = first;
-      ring[0] = first;
-      uint32_t pos = W;
-      for (uint32_t i = 1; i < n; ++i) {
-        if (avail - pos < 2) {
+    uint32_t q = W, i = 1; // stream position of value i
+    while (i < n && rc == 0) {
+      if (avail - q >= 34) {
+        // window: lane L reads the header that would start at q + L
+        const uint32_t h = uint32_t(src[q + lane]) | (uint32_t(src[q + lane + 1]) << 8);
+        uint32_t sig = (h >> 6) & 7;
+        const uint32_t tz = h & 63, ref = h >> 9;
+        if (tz < 63 && sig == 0) sig = 8; // unpack(), patas.rs:158-160
+        const uint32_t pack = (lane + 2 + sig) | (sig > uint32_t(W) ? 0x80u : 0u) | (ref << 8);
+        uint32_t p = 0, cnt = 0, myp = 0;
+#pragma unroll
+        for (uint32_t hop = 0; hop < 16; ++hop) { // a value takes >= 2 stream bytes
+          const uint32_t v = __shfl_sync(0xffffffffu, pack, p);
+          const uint32_t r = v >> 8, nx = v & 0x7fu;
+          if ((v & 0x80u) || r == 0 || r > i || avail - q < nx) { // sig > W, bad reference, payload past the end
+            rc = SB_PANIC;
+            break;
+          }
+          if (lane == hop) myp = q + p;
+          p = nx;
+          ++cnt;
+          ++i;
+          if (p >= 32 || i >= n) break;
+        }
+        if (lane < cnt) pos[i - cnt + lane] = myp;
+        q += p;
+      } else {
+        // tail of the stream: one value at a time, the reference's checks in its order
+        if (avail - q < 2) {
           rc = SB_IO;
           break;
         }
-        uint32_t p = ld_u16u(src + pos);
-        pos += 2;
-        uint32_t ref = (p >> 9) & 0x7f, sig = (p >> 6) & 7, tz = p & 0x3f;
-        if (tz < 63 && sig == 0) sig = 8; // unpack(), patas.rs:158-160
-        if (sig > uint32_t(W) || avail - pos < sig || ref == 0 || ref > i) { // App. C4 / OOB index panics
+        const uint32_t h = ld_u16u(src + q);
+        uint32_t sig = (h >> 6) & 7;
+        const uint32_t tz = h & 63, ref = h >> 9;
+        if (tz < 63 && sig == 0) sig = 8;
+        if (sig > uint32_t(W) || avail - q - 2 < sig || ref == 0 || ref > i) {
           rc = SB_PANIC;
           break;
         }
-        uint64_t val = 0;
-        for (uint32_t b = 0; b < sig; ++b) val |= uint64_t(src[pos + b]) << (8 * b);
-        pos += sig;
-        uint64_t prev = ring[(i - ref) & 127];
-        uint64_t x = (val << tz) ^ prev;
-        if (W == 4) x &= 0xffffffffull;
-        out[i] = T(x);
-        ring[i & 127] = x;
+        if (lane == 0) pos[i] = q;
+        q += 2 + sig;
+        ++i;
       }
     }
-    cx.bcast[0] = rc;
+    if (lane == 0) cx.bcast[0] = rc;
   }
   __syncthreads();
-  cx.ar = mark;
   int rc = cx.bcast[0];
   if (rc) {
+    cx.ar = mark;
     cx.flag(rc);
     return false;
   }
+  // ---- 2. values, 128 per step
+  T *out = reinterpret_cast<T *>(dst);
+  const uint64_t first = uint64_t(ld_elem_u<W>(src));
+  for (uint32_t c0 = 0; c0 < n; c0 += SB_NT) {
+    const uint32_t i = c0 + tid;
+    uint64_t acc = 0;
+    uint32_t ptr = 0xffffffffu; // in-step index of the value this one still needs; 0xffffffff = final
+    if (i == 0) {
+      acc = first;
+    } else if (i < n) {
+      const uint32_t at = pos[i];
+      const uint32_t h = ld_u16u(src + at);
+      uint32_t sig = (h >> 6) & 7;
+      const uint32_t tz = h & 63, ref = h >> 9;
+      if (tz < 63 && sig == 0) sig = 8;
+      uint64_t val = 0;
+      for (uint32_t b = 0; b < sig; ++b) val |= uint64_t(src[at + 2 + b]) << (8 * b);
+      acc = val << tz;
+      const uint32_t P = i - ref;
+      if (P < c0) acc ^= hist[P & 255]; // an earlier step: final
+      else ptr = P - c0;
+    }
+    // pointer jumping inside the step: references point strictly backwards, <= 7 rounds
+    for (uint32_t round = 0;; ++round) {
+      uint64_t *ab = acc_s + (round & 1) * SB_NT;
+      uint32_t *pb = ptr_s + (round & 1) * SB_NT;
+      ab[tid] = acc;
+      pb[tid] = ptr;
+      if (!__syncthreads_or(ptr != 0xffffffffu)) break;
+      if (ptr != 0xffffffffu) {
+        acc ^= ab[ptr];
+        ptr = pb[ptr];
+      }
+    }
+    if (i < n) {
+      if (W == 4) acc &= 0xffffffffull;
+      out[i] = T(acc);
+      hist[i & 255] = acc;
+    }
+    __syncthreads();
+  }
+  cx.ar = mark;
   return true;
 }
 
