@@ -222,3 +222,33 @@ def test_corrupt_pages_report_status(ctx):
         assert res.page_status[0] != 0 and res.page_status[1] == 0
         with pytest.raises(sb.StrawboatError):
             ctx.decode_columns([sb.Column(sb.I32, False, bytes(bad), metas)])
+
+
+def test_concurrent_contexts(ctx):
+    """one context per host thread (the reference's readers are per-task objects, deserialize.rs:28):
+    calls on different contexts overlap on the device and must not disturb each other"""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(12)
+    jobs = []
+    for i, t in enumerate([sbo.I32, sbo.I64, sbo.F64, sbo.I16, sbo.U8, sbo.F32]):
+        v = rand_values(rng, t, 40_000 + 13 * i, 200 if i % 2 else None)
+        val = rng.random(len(v)) > 0.3 if i % 3 == 0 else None
+        data, metas = oracle_encode_column(t, v, val, page_size=2048, opts=sbo.make_opts(sbo.C_LZ4, ratio=2.0))
+        jobs.append((t, val is not None, data, metas, oracle_decode_column(t, val is not None, data, metas)))
+    ctxs = [sb.Context(0) for _ in range(3)]
+
+    def work(k):
+        out = []
+        for rep in range(4):
+            for j in range(k, len(jobs), len(ctxs)):
+                t, nu, data, metas, _ = jobs[j]
+                out.append((j, ctxs[k].batch_read_array(sb.Column(t, nu, data, metas))))
+        return out
+
+    with ThreadPoolExecutor(len(ctxs)) as ex:
+        results = list(ex.map(work, range(len(ctxs))))
+    for res in results:
+        for j, dec in res:
+            assert_same(dec, jobs[j][4], jobs[j][0], jobs[j][1])
+    for c in ctxs:
+        c.close()
