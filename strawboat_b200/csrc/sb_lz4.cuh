@@ -288,7 +288,7 @@ struct Lz4Scan {
       if (seq + n - c_seen <= SB_LZ4_Q) break;
       publish();
       if (aborted()) return false;
-      __nanosleep(256);
+      __nanosleep(2000); // the queue holds 8 mover batches (~20 us of work): no need to poll fast
     }
     return true;
   }
