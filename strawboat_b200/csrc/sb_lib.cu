@@ -461,9 +461,10 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       if (m.length + 32 <= stage_cap) {
         n_items += 1;
         max_stage = std::max<uint32_t>(max_stage, uint32_t(m.length));
-        // a page that is much smaller than its decoded size is Dict / Freq / RLE coded: give its
+        // a page less than half its decoded size is Dict / Freq / RLE coded (binary: any page): give its
         // index buffer (4 bytes per row) room in shared memory instead of the L2 scratch
-        if (m.length < m.num_values * W) max_need = std::max<uint64_t>(max_need, m.length + 4 * m.num_values + 16 * 1024);
+        if (col_binary(ci) || 2 * m.length < m.num_values * W)
+          max_need = std::max<uint64_t>(max_need, m.length + 4 * m.num_values + 16 * 1024);
       } else {
         uint64_t out_bytes = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * W;
         bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type) && !col_nested(ci);
