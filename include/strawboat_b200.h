@@ -198,6 +198,15 @@ typedef struct {
   const void *offsets;         /* binary: length+1 offsets */
   const uint8_t *validity;     /* may be NULL */
   int32_t mem;
+  /* Nested leaves (leaf.n_nested > 1) only; all zero for flat leaves.  The Dremel levels of
+   * the whole column in row order -- what arrow2's write_rep_and_def iterates over the
+   * `Nested` descriptors (src/write/serialize.rs:217-232).  `length` is then the number of
+   * LEAF SLOTS, `rows` the number of top-level rows pages are cut by (write/common.rs:79-86);
+   * rep_levels may be NULL when the column has no list depth (max_rep == 0). */
+  const uint32_t *rep_levels;
+  const uint32_t *def_levels;
+  uint64_t n_levels;
+  uint64_t rows;
 } sb_leaf_array;
 
 typedef struct {
@@ -209,11 +218,15 @@ typedef struct {
   void *_owner;
 } sb_encoded_column;
 
-/* Replaces the page loop of NativeWriter::encode_chunk for flat leaves
+/* Replaces the page loop of NativeWriter::encode_chunk
  * (src/write/common.rs:71-115 -> write::write, src/write/serialize.rs:36-132 ->
  * compress_integer / compress_double / compress_binary / compress_boolean): slices each
  * leaf into pages of max_page_size rows, chooses a codec per page as choose_compressor
- * does, and emits the page bytes plus the PageMeta{length,num_values} the footer needs. */
+ * does, and emits the page bytes plus the PageMeta{length,num_values} the footer needs.
+ * Nested leaves (write_nested + write_nested_validity, src/write/serialize.rs:135-198,
+ * 217-232): pages are cut by top-level rows; each page is
+ * [u32 rows][u32 rep_len][u32 def_len][rep stream][def stream][VALUE_BLOCK over the page's
+ * leaf slots], PageMeta.num_values = level entries of the page. */
 int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_cols,
                           const sb_write_options *opts, int32_t out_mem, sb_encoded_column *outs);
 void sb_release_encoded(sb_ctx *ctx, sb_encoded_column *outs, uint64_t n);

@@ -267,10 +267,31 @@ class LeafArray:
                `packed_validity`; device tensors are always packed), or None
     """
 
-    def __init__(self, type_, values, validity=None, nullable=None, length=None, packed_validity=False):
+    def __init__(self, type_, values, validity=None, nullable=None, length=None, packed_validity=False,
+                 nested=None, rep_levels=None, def_levels=None, rows=None):
+        """nested leaves: `nested` = [(kind, nullable)] root -> leaf, `rep_levels` / `def_levels` = the
+        column's Dremel levels (uint32, host arrays or CUDA tensors), `rows` = top-level rows; `values` /
+        `validity` then cover the leaf slots."""
         self.type = type_
         self.nullable = (validity is not None) if nullable is None else bool(nullable)
         self._keep = []
+        self.nested = nested
+        self.rep_ptr = self.def_ptr = 0
+        self.n_levels = 0
+        self.rows = 0 if rows is None else int(rows)
+        if nested:
+            for name, lv in (("rep_ptr", rep_levels), ("def_ptr", def_levels)):
+                if lv is None:
+                    continue
+                if hasattr(lv, "data_ptr"):
+                    self._keep.append(lv)
+                    setattr(self, name, lv.data_ptr())
+                    self.n_levels = lv.numel()
+                else:
+                    a = np.ascontiguousarray(lv, dtype=np.uint32)
+                    self._keep.append(a)
+                    setattr(self, name, a.ctypes.data if a.size else 0)
+                    self.n_levels = len(a)
         self.offsets_ptr = 0
         self.values_bytes = 0
         self.mem = MEM_HOST
@@ -346,7 +367,11 @@ def _encode_columns(self, arrays, options=None, out="host"):
     n = len(arrays)
     ins = (_capi.LeafArray * n)()
     for i, a in enumerate(arrays):
-        ins[i].leaf = make_leaf(a.type, a.nullable)
+        ins[i].leaf = make_leaf(a.type, a.nullable, a.nested)
+        ins[i].rep_levels = a.rep_ptr
+        ins[i].def_levels = a.def_ptr
+        ins[i].n_levels = a.n_levels
+        ins[i].rows = a.rows
         ins[i].length = a.length
         ins[i].values = a.values_ptr
         ins[i].values_bytes = a.values_bytes

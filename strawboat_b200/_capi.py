@@ -58,7 +58,8 @@ class WriteOptions(C.Structure):
 
 class LeafArray(C.Structure):
     _fields_ = [("leaf", Leaf), ("length", C.c_uint64), ("values", C.c_void_p), ("values_bytes", C.c_uint64),
-                ("offsets", C.c_void_p), ("validity", C.c_void_p), ("mem", C.c_int32)]
+                ("offsets", C.c_void_p), ("validity", C.c_void_p), ("mem", C.c_int32),
+                ("rep_levels", C.c_void_p), ("def_levels", C.c_void_p), ("n_levels", C.c_uint64), ("rows", C.c_uint64)]
 
 
 class EncodedColumn(C.Structure):

@@ -184,7 +184,8 @@ __device__ __forceinline__ bool bin_header(Dctx &cx, const uint8_t *src, uint32_
 // offset; `tab` = this page's slice of the entry table (global).
 // =========================================================================================
 __device__ bool binary_page_size(Dctx &cx, const uint8_t *page, uint32_t page_len, uint32_t vb, uint32_t n, BinEntry *tab,
-                                 uint64_t *out_bytes) {
+                                 uint64_t *out_bytes, uint32_t *val_pos) {
+  *val_pos = 0;
   BinBlock b;
   if (!bin_header(cx, page + vb, page_len - vb, &b)) return false;
   const uint32_t body_pos = vb + 9;
@@ -196,6 +197,10 @@ __device__ bool binary_page_size(Dctx &cx, const uint8_t *page, uint32_t page_le
       return false;
     }
     *out_bytes = ld_u32u(b.body + b.compressed + 5);
+    // plain value bytes can be copied by several work items (tiles): position of the first one
+    const uint32_t c2 = ld_u32u(b.body + b.compressed + 1);
+    if (b.codec == SB_C_NONE && c2 == uint32_t(*out_bytes) && c2 <= b.body_avail - b.compressed - 9)
+      *val_pos = body_pos + b.compressed + 9;
     return true;
   }
   case SB_C_ZSTD:
@@ -392,7 +397,7 @@ __device__ __forceinline__ const BinEntry *stage_entries(Dctx &cx, const BinEntr
 template <int OW>
 __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, uint32_t vb, uint32_t n,
                               typename OffT<OW>::T *out_off, uint8_t *out_val, uint64_t base, bool first,
-                              const BinEntry *tab) {
+                              const BinEntry *tab, bool values_tiled) {
   using O = typename OffT<OW>::T;
   BinBlock b;
   if (!bin_header(cx, page + vb, page_len - vb, &b)) return false;
@@ -441,14 +446,7 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
         return w;
       };
       const uint8_t *rv = raw + uint64_t(j0 + head) * OW;
-      uint4 *ov = reinterpret_cast<uint4 *>(out_off + j0 + head);
-      uint32_t v = tid;
-      for (; v + 3 * SB_NT < nvec; v += 4 * SB_NT) { // four vectors in flight per thread
-        uint4 a = ld_u128u(rv + (uint64_t(v) << 4)), b = ld_u128u(rv + (uint64_t(v + SB_NT) << 4));
-        uint4 c = ld_u128u(rv + (uint64_t(v + 2 * SB_NT) << 4)), e = ld_u128u(rv + (uint64_t(v + 3 * SB_NT) << 4));
-        ov[v] = rebase(a), ov[v + SB_NT] = rebase(b), ov[v + 2 * SB_NT] = rebase(c), ov[v + 3 * SB_NT] = rebase(e);
-      }
-      for (; v < nvec; v += SB_NT) ov[v] = rebase(ld_u128u(rv + (uint64_t(v) << 4)));
+      stream_vec(cx, reinterpret_cast<uint4 *>(out_off + j0 + head), rv, nvec, [&](uint4 w, uint64_t) { return rebase(w); });
       for (uint32_t j = j0 + head + nvec * E + tid; j <= n; j += SB_NT) scalar(j);
     }
     __syncthreads();
@@ -464,6 +462,7 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
       cx.flag(SB_IO);
       return false;
     }
+    if (values_tiled && b.codec == SB_C_NONE && c2 == u2) return true; // value bytes: tiles 1.. of this page
     return dec_basic(cx, b.codec, h2 + 9, c2, out_val, u2);
   }
   case SB_C_ZSTD:

@@ -37,6 +37,8 @@ struct PageDesc {
 // into PageDesc.out_elem / out_byte and base[] before pass 1.
 struct PageAux {
   uint64_t value_bytes;
+  uint32_t val_pos; // binary Basic / None pages: page position of the plain value bytes (0 = not tileable)
+  uint32_t pad;
   uint32_t cnt[SB_MAX_NESTED];
   uint64_t base[SB_MAX_NESTED];
 };
@@ -297,6 +299,8 @@ struct Dctx {
   int *bcast;        // shared: 4 ints for CTA-wide broadcasts
   const uint8_t *page_s = nullptr; // first byte of the page as the decoders see it (shared when staged)
   const uint8_t *page_g = nullptr; // the same byte in global memory (source of cp.async streams)
+  uint64_t *rbar = nullptr;        // shared: SB_RING_STAGES mbarriers of the streaming ring (nullptr = no ring)
+  uint32_t rphase = 0;             // their phase bits (CTA-uniform, carried across pages)
   __device__ __forceinline__ void flag(int code) { atomicCAS(err, 0, code); }
 };
 
@@ -330,6 +334,87 @@ __device__ __forceinline__ void copy_bytes(uint8_t *dst, const uint8_t *src, uin
     }
     for (; v < nvec; v += SB_NT) d[v] = ld_u128u(src + (v << 4));
   }
+  for (uint64_t i = (nvec << 4) + tid; i < nbytes; i += SB_NT) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------
+// Streaming ring: pages that do not fit the staging buffer are pulled through shared memory
+// in SB_RING_CHUNK pieces by the TMA engine (SB_RING_STAGES bulk loads in flight per CTA),
+// realigned with funnel shifts and written with aligned 16-byte stores.  `f(vec, index)`
+// transforms every 16-byte vector (identity for copies, offset rebase for binary pages).
+// `d` is 16-byte aligned, `src` any byte address; nvec vectors are produced.
+// ------------------------------------------------------------------------------------
+#define SB_RING_STAGES 4
+#define SB_RING_CHUNK 8192
+
+template <class F>
+__device__ __forceinline__ void stream_vec(Dctx &cx, uint4 *d, const uint8_t *src, uint64_t nvec, F f) {
+  const uint32_t tid = threadIdx.x;
+  constexpr uint32_t VPC = SB_RING_CHUNK / 16, SLOT = SB_RING_CHUNK + 16;
+  Arena mark = cx.ar;
+  uint8_t *ring = nullptr;
+  if (cx.rbar != nullptr && nvec >= 2 * VPC && __isGlobal(src))
+    ring = static_cast<uint8_t *>(cx.ar.alloc_shared(SB_RING_STAGES * SLOT));
+  if (!ring) { // small, or the source already sits in shared memory
+    uint64_t v = tid;
+    for (; v + 3 * SB_NT < nvec; v += 4 * SB_NT) {
+      uint4 a = ld_u128u(src + (v << 4)), b = ld_u128u(src + ((v + SB_NT) << 4));
+      uint4 c = ld_u128u(src + ((v + 2 * SB_NT) << 4)), e = ld_u128u(src + ((v + 3 * SB_NT) << 4));
+      d[v] = f(a, v), d[v + SB_NT] = f(b, v + SB_NT), d[v + 2 * SB_NT] = f(c, v + 2 * SB_NT), d[v + 3 * SB_NT] = f(e, v + 3 * SB_NT);
+    }
+    for (; v < nvec; v += SB_NT) d[v] = f(ld_u128u(src + (v << 4)), v);
+    return;
+  }
+  const uint32_t a = uint32_t(uintptr_t(src) & 15);
+  const uint8_t *g = src - a;
+  const uint64_t nch = (nvec + VPC - 1) / VPC;
+  auto issue = [&](uint64_t c) { // thread 0: chunk c -> slot c % STAGES
+    const uint32_t s = uint32_t(c % SB_RING_STAGES);
+    const uint64_t v0 = c * VPC;
+    const uint32_t nv = uint32_t(min(uint64_t(VPC), nvec - v0));
+    const uint32_t bytes = nv * 16 + (a ? 16u : 0u); // only granules that hold requested bytes
+    mbar_expect_tx(cx.rbar + s, bytes);
+    tma_load_1d(ring + s * SLOT, g + (v0 << 4), bytes, cx.rbar + s);
+  };
+  __syncthreads(); // earlier generic accesses to this part of the arena are done
+  if (tid == 0) {
+    fence_proxy_async();
+    for (uint64_t c = 0; c < nch && c < SB_RING_STAGES; ++c) issue(c);
+  }
+  for (uint64_t c = 0; c < nch; ++c) {
+    const uint32_t s = uint32_t(c % SB_RING_STAGES);
+    mbar_wait(cx.rbar + s, (cx.rphase >> s) & 1u);
+    cx.rphase ^= 1u << s;
+    const uint8_t *sp = ring + s * SLOT + a;
+    const uint64_t v0 = c * VPC;
+    const uint32_t nv = uint32_t(min(uint64_t(VPC), nvec - v0));
+    if (nv == VPC) {
+      static_assert(VPC == 4 * SB_NT, "one chunk = four vectors per thread");
+      uint4 x0 = ld_u128u(sp + (tid << 4)), x1 = ld_u128u(sp + ((tid + SB_NT) << 4));
+      uint4 x2 = ld_u128u(sp + ((tid + 2 * SB_NT) << 4)), x3 = ld_u128u(sp + ((tid + 3 * SB_NT) << 4));
+      uint4 *dd = d + v0 + tid;
+      dd[0] = f(x0, v0 + tid), dd[SB_NT] = f(x1, v0 + tid + SB_NT);
+      dd[2 * SB_NT] = f(x2, v0 + tid + 2 * SB_NT), dd[3 * SB_NT] = f(x3, v0 + tid + 3 * SB_NT);
+    } else {
+      for (uint32_t i = tid; i < nv; i += SB_NT) d[v0 + i] = f(ld_u128u(sp + (i << 4)), v0 + i);
+    }
+    __syncthreads(); // slot s fully read
+    if (tid == 0 && c + SB_RING_STAGES < nch) {
+      fence_proxy_async();
+      issue(c + SB_RING_STAGES);
+    }
+  }
+  cx.ar = mark;
+}
+
+// copy_bytes for sources that may be large and in global memory (unstaged pages)
+__device__ __forceinline__ void stream_copy(Dctx &cx, uint8_t *dst, const uint8_t *src, uint64_t nbytes) {
+  const uint32_t tid = threadIdx.x;
+  uint64_t head = min(nbytes, uint64_t((16 - (uintptr_t(dst) & 15)) & 15));
+  for (uint64_t i = tid; i < head; i += SB_NT) dst[i] = src[i];
+  dst += head, src += head, nbytes -= head;
+  const uint64_t nvec = nbytes >> 4;
+  stream_vec(cx, reinterpret_cast<uint4 *>(dst), src, nvec, [](uint4 v, uint64_t) { return v; });
   for (uint64_t i = (nvec << 4) + tid; i < nbytes; i += SB_NT) dst[i] = src[i];
 }
 

@@ -111,7 +111,7 @@ __device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *sr
       cx.flag(SB_PANIC);
       return false;
     }
-    copy_bytes(dst, src, out_bytes);
+    stream_copy(cx, dst, src, out_bytes);
     return true;
   }
   if (codec == SB_C_LZ4) return dec_lz4_block(cx, src, clen, dst, out_bytes);

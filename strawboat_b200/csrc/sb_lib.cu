@@ -30,6 +30,7 @@ constexpr uint32_t kSmemMin = 40 * 1024;
 constexpr uint32_t kArenaMin = 6 * 1024;     // arena left after the largest staged page
 constexpr uint32_t kTileBytes = 64 * 1024;   // output bytes per work item of an unstaged page
 constexpr uint32_t kTmaChunk = 32 * 1024;
+constexpr uint32_t kBinTile = 32 * 1024;     // plain value bytes per work item of an unstaged binary page
 
 
 
@@ -65,7 +66,23 @@ __device__ __forceinline__ bool lz4_side_page(const uint8_t *p, uint32_t len, bo
   return true;
 }
 
-// side_flags: 0 = decoded by the main kernel, 1 = top-level LZ4 block -> sb_lz4_kernel,
+// [validity section][hdr9 codec None][n * W value bytes]: a page that is one plain copy
+__device__ __forceinline__ bool plain_page(const uint8_t *p, uint32_t len, bool nullable, uint64_t out_bytes) {
+  uint32_t vb = 0;
+  if (nullable) {
+    if (len < 4) return false;
+    uint32_t L = uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
+    if (L > len - 4) return false;
+    vb = 4 + L;
+  }
+  if (len - vb < 9 || p[vb] != SB_C_NONE) return false;
+  const uint8_t *h = p + vb;
+  uint32_t clen = uint32_t(h[1]) | (uint32_t(h[2]) << 8) | (uint32_t(h[3]) << 16) | (uint32_t(h[4]) << 24);
+  return clen <= len - vb - 9 && uint64_t(clen) == out_bytes && out_bytes >= 4 * SB_RING_CHUNK;
+}
+
+// side_flags: 0 = decoded by the main kernel, 3 = plain page (codec None): streamed through the TMA ring
+// instead of being staged whole, 1 = top-level LZ4 block -> sb_lz4_kernel,
 // 2 = "stored" LZ4 block (one literal run covering the whole output: what LZ4 emits for
 // incompressible data) -> plain copy in the main kernel.
 // Jobs are binned by compressed size: long streams from the front of `jobs`, short ones from
@@ -89,6 +106,10 @@ __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const Col
   const ColDesc col = cols[pg.col];
   if (!is_fixed_type(col.type) || col.n_nested > 1) return;
   uint32_t vb, clen;
+  if (plain_page(pg.src, pg.len, col.nullable != 0, uint64_t(pg.num_values) * uint32_t(col.W))) {
+    if (lane == 0) side_flags[i] = 3;
+    return;
+  }
   if (!lz4_side_page(pg.src, pg.len, col.nullable != 0, &vb, &clen)) return;
   const uint64_t dlen64 = uint64_t(pg.num_values) * uint32_t(col.W);
   if (dlen64 > SB_LZ4_MAXPOS / 2 || clen > SB_LZ4_MAXPOS / 2) return; // positions are 30-bit in sb_lz4_kernel
@@ -160,6 +181,7 @@ __global__ void __launch_bounds__(SB_NT, 4)
                      const uint8_t *__restrict__ side_flags, PageAux *aux, BinEntry *entries, uint32_t *codec_hist, int pass) {
   extern __shared__ __align__(128) uint8_t dsm[];
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_rbar[SB_RING_STAGES];
   __shared__ int s_err;
   __shared__ uint32_t s_ws[SB_NWARP + 1];
   __shared__ int s_bcast[4];
@@ -168,19 +190,20 @@ __global__ void __launch_bounds__(SB_NT, 4)
   const uint32_t tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
+    for (int i = 0; i < SB_RING_STAGES; ++i) mbar_init(&s_rbar[i], 1);
     fence_mbar_init();
+    s_item = atomicAdd(counter, 1u);
+    s_err = 0;
   }
   __syncthreads();
-  uint32_t phase = 0;
+  uint32_t phase = 0, ring_phase = 0;
 
   for (;;) {
-    if (tid == 0) {
-      s_item = atomicAdd(counter, 1u);
-      s_err = 0;
-    }
-    __syncthreads();
     const uint32_t it = s_item;
     if (it >= n_items) break;
+    // the next item's ticket is drawn now and travels under this item's work
+    uint32_t next_it = 0;
+    if (tid == 0) next_it = atomicAdd(counter, 1u);
     const WorkItem wi = items[it];
     const PageDesc pg = pages[wi.page];
     const ColDesc &col = cols[pg.col];
@@ -190,9 +213,14 @@ __global__ void __launch_bounds__(SB_NT, 4)
     if (lz4_side && !col.nullable) { // value block handled by sb_lz4_kernel, nothing else in the page
       if (tid == 0 && (wi.tile == 0 || wi.tile == 0xffffffffu)) atomicAdd(codec_hist + SB_C_LZ4, 1u);
       __syncthreads();
+      if (tid == 0) s_item = next_it;
+      __syncthreads();
       continue;
     }
-    const bool staged = pg.len + 32 <= stage_cap;
+    const bool plain = side == 3;    // codec None, header validated by sb_classify_kernel
+    // plain pages stage only what precedes the value bytes (validity section + hdr9; nothing when not nullable)
+    const uint32_t stage_len = plain ? pg.len - pg.num_values * uint32_t(col.W) : pg.len;
+    const bool staged = stage_len + 32 <= stage_cap && !(plain && !col.nullable);
 
     Dctx cx;
     cx.err = &s_err;
@@ -201,11 +229,13 @@ __global__ void __launch_bounds__(SB_NT, 4)
     cx.ar.g_cur = scratch + uint64_t(blockIdx.x) * scratch_per_cta;
     cx.ar.g_end = cx.ar.g_cur + scratch_per_cta;
     cx.ar.s_end = dsm + smem_bytes;
+    cx.rbar = s_rbar;
+    cx.rphase = ring_phase;
 
     const uint8_t *p;
     if (staged) {
       const uint32_t mis = uint32_t(uintptr_t(pg.src) & 15);
-      const uint32_t bytes = (mis + pg.len + 15) & ~15u;
+      const uint32_t bytes = (mis + stage_len + 15) & ~15u;
       if (tid == 0 && bytes) {
         fence_proxy_async();
         mbar_expect_tx(&s_bar, bytes);
@@ -233,6 +263,9 @@ __global__ void __launch_bounds__(SB_NT, 4)
 
     if (col.type == SB_NULL) {
       // null.rs: length only, nothing to decode
+    } else if (plain && !col.nullable && wi.tile == 0xffffffffu) {
+      if (tid == 0) atomicAdd(codec_hist + SB_C_NONE, 1u);
+      stream_copy(cx, col.values + pg.out_elem * uint64_t(col.W), p + 9, uint64_t(n) * uint32_t(col.W));
     } else if (pass == 1 && !staged && wi.tile != 0xffffffffu && flat_fixed && !col.nullable) {
       // ---- oversized page (e.g. max_page_size = None): None / OneValue are split into
       //      tiles that stream straight from global memory; anything else runs on tile 0.
@@ -244,10 +277,10 @@ __global__ void __launch_bounds__(SB_NT, 4)
       uint8_t *dst = col.values + pg.out_elem * W;
       if (wi.tile == 0 && tid == 0 && codec >= 0 && codec < 32) atomicAdd(codec_hist + codec, 1u);
       if (codec == SB_C_NONE && avail >= 9 && compressed <= avail - 9 && uint64_t(compressed) == uint64_t(n) * W) {
-        copy_bytes(dst + uint64_t(lo) * W, p + 9 + uint64_t(lo) * W, uint64_t(hi - lo) * W);
+        stream_copy(cx, dst + uint64_t(lo) * W, p + 9 + uint64_t(lo) * W, uint64_t(hi - lo) * W);
       } else if (stored) { // validated by sb_classify_kernel: [token 0xF0][ne length bytes][n*W literals]
         const uint32_t lit0 = 9 + 1 + ((n * W - 15) / 255 + 1);
-        copy_bytes(dst + uint64_t(lo) * W, p + lit0 + uint64_t(lo) * W, uint64_t(hi - lo) * W);
+        stream_copy(cx, dst + uint64_t(lo) * W, p + lit0 + uint64_t(lo) * W, uint64_t(hi - lo) * W);
       } else if (codec == SB_C_ONEVALUE && avail >= 9 + W) {
         switch (W) {
         case 1: dec_onevalue<1>(cx, p + 9, avail - 9, lo, hi, dst); break;
@@ -259,6 +292,12 @@ __global__ void __launch_bounds__(SB_NT, 4)
         uint32_t used = 0;
         if (!lz4_side) ok = decode_fixed<0>(cx, p, avail, n, col.W, col.is_float != 0, dst, &used);
       }
+    } else if (pass == 1 && !staged && wi.tile != 0xffffffffu && wi.tile != 0 && is_binary_type(col.type) && !nested) {
+      // ---- oversized binary page, tiles 1..: a slice of the plain value bytes found by the plan pass
+      const PageAux &ax = aux[pg.aux];
+      const uint64_t lo = uint64_t(wi.tile - 1) * kBinTile;
+      if (ax.val_pos != 0 && lo < ax.value_bytes)
+        stream_copy(cx, col.values + pg.out_byte + lo, p + ax.val_pos + lo, min(uint64_t(kBinTile), ax.value_bytes - lo));
     } else if (wi.tile == 0 || wi.tile == 0xffffffffu) {
       PageAux *ax = pg.aux != 0xffffffffu ? aux + pg.aux : nullptr;
       uint32_t vb = 0;
@@ -280,11 +319,17 @@ __global__ void __launch_bounds__(SB_NT, 4)
         if (vb == 0xffffffffu) ok = false;
       }
       if (ok && pass == 1 && tid == 0 && avail > vb && p[vb] < 32) atomicAdd(codec_hist + p[vb], 1u);
+      // plain value bytes of an oversized flat binary page travel as tiles 1.. (same predicate as the host's item list)
+      const bool vtiled = pass == 1 && !staged && wi.tile == 0 && is_binary_type(col.type) && !nested && ax && ax->val_pos != 0;
       if (ok && pass == 0) {
         if (is_binary_type(col.type)) {
           uint64_t vbytes = 0;
-          ok = binary_page_size(cx, p, avail, vb, n, entries + pg.tab_off, &vbytes);
-          if (tid == 0) ax->value_bytes = ok ? vbytes : 0;
+          uint32_t val_pos = 0;
+          ok = binary_page_size(cx, p, avail, vb, n, entries + pg.tab_off, &vbytes, &val_pos);
+          if (tid == 0) {
+            ax->value_bytes = ok ? vbytes : 0;
+            ax->val_pos = ok ? val_pos : 0;
+          }
         } else if (tid == 0) {
           ax->value_bytes = 0;
         }
@@ -296,24 +341,32 @@ __global__ void __launch_bounds__(SB_NT, 4)
           // top-level LZ4 blocks are decoded by sb_lz4_kernel (same predicate as sb_classify_kernel)
           if (stored) {
             const uint32_t dlen = n * uint32_t(col.W);
-            copy_bytes(col.values + out_elem * uint64_t(col.W), p + vb + 9 + 1 + ((dlen - 15) / 255 + 1), dlen);
+            stream_copy(cx, col.values + out_elem * uint64_t(col.W), p + vb + 9 + 1 + ((dlen - 15) / 255 + 1), dlen);
+          } else if (plain) { // value bytes stream from global memory behind the staged validity section
+            stream_copy(cx, col.values + out_elem * uint64_t(col.W), pg.src + vb + 9, uint64_t(n) * uint32_t(col.W));
           } else if (!lz4_side)
             ok = decode_fixed<0>(cx, p + vb, avail - vb, n, col.W, col.is_float != 0,
                                  col.values + out_elem * uint64_t(col.W), &used);
         } else if (col.type == SB_BINARY) {
           ok = decode_binary<4>(cx, p, avail, vb, n, reinterpret_cast<int32_t *>(col.offsets) + out_elem,
-                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off);
+                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off, vtiled);
         } else if (col.type == SB_LARGE_BINARY) {
           ok = decode_binary<8>(cx, p, avail, vb, n, reinterpret_cast<int64_t *>(col.offsets) + out_elem,
-                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off);
+                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off, vtiled);
         } else {
           cx.flag(SB_NYI);
         }
       }
     }
     (void)ok;
+    ring_phase = cx.rphase;
     __syncthreads(); // all reads of the staged page / arena done before the next TMA lands
-    if (tid == 0 && s_err) atomicCAS(status + wi.page, 0, s_err);
+    if (tid == 0) {
+      if (s_err) atomicCAS(status + wi.page, 0, s_err);
+      s_err = 0;
+      s_item = next_it;
+    }
+    __syncthreads();
   }
 }
 
@@ -468,7 +521,8 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       } else {
         uint64_t out_bytes = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * W;
         bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type) && !col_nested(ci);
-        n_items += tiled ? std::max<uint64_t>(1, (out_bytes + kTileBytes - 1) / kTileBytes) : 1;
+        if (col_binary(ci) && !col_nested(ci)) n_items += 1 + (m.length + kBinTile - 1) / kBinTile; // tile 0 + value slices
+        else n_items += tiled ? std::max<uint64_t>(1, (out_bytes + kTileBytes - 1) / kTileBytes) : 1;
       }
       if (plan) n_plan += 1;
       if (col_binary(ci)) n_entries += m.length / 8 + 1;
@@ -629,6 +683,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
         uint64_t out_b = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * uint64_t(std::max(1, W));
         bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type) && !nested;
         uint64_t nt = tiled ? std::max<uint64_t>(1, (out_b + kTileBytes - 1) / kTileBytes) : 1;
+        if (binary && !nested) nt = 1 + (m.length + kBinTile - 1) / kBinTile;
         for (uint64_t t = 0; t < nt; ++t) h_items[ii++] = WorkItem{uint32_t(pi), uint32_t(t)};
       }
       src_off += m.length;

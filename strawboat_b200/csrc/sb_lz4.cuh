@@ -171,6 +171,9 @@ template <class Out> __device__ int lz4_decode_warp2(const uint8_t *src, uint32_
 constexpr uint32_t SB_LZ4_INR = 4096;       // input ring bytes
 constexpr uint32_t SB_LZ4_INCH = 1024;      // refill granularity
 constexpr uint32_t SB_LZ4_Q = 256;          // queue entries (u32 each)
+#ifndef SB_LZ4_SLACK
+#define SB_LZ4_SLACK 96                     // entries the mover retires before a blocked scanner resumes
+#endif
 constexpr uint32_t SB_LZ4_NEAR = SB_LZ4_RING - 2048 - 64; // match distance served from the ring
 constexpr uint32_t SB_LZ4_FLUSHQ = 1024;    // write-behind granularity
 constexpr uint32_t SB_LZ4_SMALL = 16;       // literal / match lengths handled one sequence per lane
@@ -281,14 +284,17 @@ struct Lz4Scan {
     }
     return true;
   }
-  // room for `n` more entries
-  __device__ bool room(uint32_t n) {
-    while (seq + n - c_seen > SB_LZ4_Q) {
+  // room for `n` more entries.  Once the queue is full the scanner stays away until the mover has
+  // retired `slack` more entries: it then scans that many sequences in one go instead of paying the
+  // housekeeping (publish / refresh / poll) once per 32-byte window.
+  __device__ bool room(uint32_t n, uint32_t slack = 0) {
+    if (seq + n - c_seen <= SB_LZ4_Q) return true;
+    publish();
+    while (seq + n + slack - c_seen > SB_LZ4_Q) {
       refresh();
-      if (seq + n - c_seen <= SB_LZ4_Q) break;
-      publish();
+      if (seq + n + slack - c_seen <= SB_LZ4_Q) break;
       if (aborted()) return false;
-      __nanosleep(2000); // the queue holds 8 mover batches (~20 us of work): no need to poll fast
+      __nanosleep(1000); // the queue holds 8 mover batches (~20 us of work): no need to poll fast
     }
     return true;
   }
@@ -331,7 +337,7 @@ __device__ int lz4_scan(const uint8_t *src, uint32_t clen, Lz4Shared *sh) {
       if (s.seq - s.pub >= 32 || s.ready != s.ready_pub) s.publish();
       s.refresh();
       s.issue_allowed();
-      if (!s.room(12) || !s.need(min(end, q + 64))) {
+      if (!s.room(12, SB_LZ4_SLACK) || !s.need(min(end, q + 64))) {
         rc = -1; // aborted by the mover (it reports the status)
         break;
       }
