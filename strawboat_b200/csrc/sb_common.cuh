@@ -348,7 +348,7 @@ __device__ __forceinline__ void copy_bytes(uint8_t *dst, const uint8_t *src, uin
 #define SB_RING_CHUNK 8192
 
 template <class F>
-__device__ __forceinline__ void stream_vec(Dctx &cx, uint4 *d, const uint8_t *src, uint64_t nvec, F f) {
+__device__ __forceinline__ void stream_vec(Dctx &cx, uint4 *d, const uint8_t *src, uint64_t nvec, F f, bool fresh = false) {
   const uint32_t tid = threadIdx.x;
   constexpr uint32_t VPC = SB_RING_CHUNK / 16, SLOT = SB_RING_CHUNK + 16;
   Arena mark = cx.ar;
@@ -376,7 +376,9 @@ __device__ __forceinline__ void stream_vec(Dctx &cx, uint4 *d, const uint8_t *sr
     mbar_expect_tx(cx.rbar + s, bytes);
     tma_load_1d(ring + s * SLOT, g + (v0 << 4), bytes, cx.rbar + s);
   };
-  __syncthreads(); // earlier generic accesses to this part of the arena are done
+  // earlier generic accesses to this part of the arena are done (`fresh`: the work item has not touched
+  // the arena yet, and the barrier at the end of the previous item covers everything before it)
+  if (!fresh) __syncthreads();
   if (tid == 0) {
     fence_proxy_async();
     for (uint64_t c = 0; c < nch && c < SB_RING_STAGES; ++c) issue(c);
@@ -408,13 +410,13 @@ __device__ __forceinline__ void stream_vec(Dctx &cx, uint4 *d, const uint8_t *sr
 }
 
 // copy_bytes for sources that may be large and in global memory (unstaged pages)
-__device__ __forceinline__ void stream_copy(Dctx &cx, uint8_t *dst, const uint8_t *src, uint64_t nbytes) {
+__device__ __forceinline__ void stream_copy(Dctx &cx, uint8_t *dst, const uint8_t *src, uint64_t nbytes, bool fresh = false) {
   const uint32_t tid = threadIdx.x;
   uint64_t head = min(nbytes, uint64_t((16 - (uintptr_t(dst) & 15)) & 15));
   for (uint64_t i = tid; i < head; i += SB_NT) dst[i] = src[i];
   dst += head, src += head, nbytes -= head;
   const uint64_t nvec = nbytes >> 4;
-  stream_vec(cx, reinterpret_cast<uint4 *>(dst), src, nvec, [](uint4 v, uint64_t) { return v; });
+  stream_vec(cx, reinterpret_cast<uint4 *>(dst), src, nvec, [](uint4 v, uint64_t) { return v; }, fresh);
   for (uint64_t i = (nvec << 4) + tid; i < nbytes; i += SB_NT) dst[i] = src[i];
 }
 

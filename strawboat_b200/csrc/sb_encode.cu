@@ -514,6 +514,7 @@ int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_col
     uint64_t *d_tot = reinterpret_cast<uint64_t *>(d_lv + lc_bytes + 3 * blk_bytes), *d_bnd = reinterpret_cast<uint64_t *>(d_lv + lc_bytes + 3 * blk_bytes + tot_bytes);
     SB_ETRY(cudaMemcpyAsync(dT, hT, off_pages, cudaMemcpyHostToDevice, st));
     SB_ETRY(cudaMemcpyAsync(d_lcols, lv_cols.data(), sizeof(LvCol) * lv_cols.size(), cudaMemcpyHostToDevice, st));
+    SB_ETRY(cudaEventRecord(ctx->ev0, st)); // device_ms of a call with nested leaves includes the level kernels (and their host round trip)
     sb_level_count_kernel<<<uint32_t(n_lv_blocks), 256, 0, st>>>(d_cols, d_lcols, uint32_t(lv_cols.size()), d_blk);
     sb_level_scan_kernel<<<uint32_t(lv_cols.size()), SB_NT, 0, st>>>(d_lcols, d_blk, d_rb, d_sb, d_tot);
     sb_level_bounds_kernel<<<uint32_t(n_lv_pages), SB_NT, 0, st>>>(d_cols, d_lcols, uint32_t(lv_cols.size()), d_rb, d_sb, d_bnd);
@@ -613,7 +614,7 @@ int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_col
     eo.force = opts->force_codec;
     eo.seed = opts->seed;
     uint32_t *d_ctr = reinterpret_cast<uint32_t *>(dT + off_ctr);
-    SB_ETRY(cudaEventRecord(ctx->ev0, st));
+    if (lv_cols.empty()) SB_ETRY(cudaEventRecord(ctx->ev0, st));
     sb_encode_kernel<<<uint32_t(grid), SB_NT, kEncSmem, st>>>(d_pages, d_cols, uint32_t(n_pages), d_ctr, static_cast<uint8_t *>(d_slab),
                                                              static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta,
                                                              reinterpret_cast<uint32_t *>(dT + off_len), reinterpret_cast<int32_t *>(dT + off_status), eo,

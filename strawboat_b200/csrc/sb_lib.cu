@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(SB_NT, 4)
       // null.rs: length only, nothing to decode
     } else if (plain && !col.nullable && wi.tile == 0xffffffffu) {
       if (tid == 0) atomicAdd(codec_hist + SB_C_NONE, 1u);
-      stream_copy(cx, col.values + pg.out_elem * uint64_t(col.W), p + 9, uint64_t(n) * uint32_t(col.W));
+      stream_copy(cx, col.values + pg.out_elem * uint64_t(col.W), p + 9, uint64_t(n) * uint32_t(col.W), true);
     } else if (pass == 1 && !staged && wi.tile != 0xffffffffu && flat_fixed && !col.nullable) {
       // ---- oversized page (e.g. max_page_size = None): None / OneValue are split into
       //      tiles that stream straight from global memory; anything else runs on tile 0.
@@ -277,10 +277,10 @@ __global__ void __launch_bounds__(SB_NT, 4)
       uint8_t *dst = col.values + pg.out_elem * W;
       if (wi.tile == 0 && tid == 0 && codec >= 0 && codec < 32) atomicAdd(codec_hist + codec, 1u);
       if (codec == SB_C_NONE && avail >= 9 && compressed <= avail - 9 && uint64_t(compressed) == uint64_t(n) * W) {
-        stream_copy(cx, dst + uint64_t(lo) * W, p + 9 + uint64_t(lo) * W, uint64_t(hi - lo) * W);
+        stream_copy(cx, dst + uint64_t(lo) * W, p + 9 + uint64_t(lo) * W, uint64_t(hi - lo) * W, true);
       } else if (stored) { // validated by sb_classify_kernel: [token 0xF0][ne length bytes][n*W literals]
         const uint32_t lit0 = 9 + 1 + ((n * W - 15) / 255 + 1);
-        stream_copy(cx, dst + uint64_t(lo) * W, p + lit0 + uint64_t(lo) * W, uint64_t(hi - lo) * W);
+        stream_copy(cx, dst + uint64_t(lo) * W, p + lit0 + uint64_t(lo) * W, uint64_t(hi - lo) * W, true);
       } else if (codec == SB_C_ONEVALUE && avail >= 9 + W) {
         switch (W) {
         case 1: dec_onevalue<1>(cx, p + 9, avail - 9, lo, hi, dst); break;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(SB_NT, 4)
       const PageAux &ax = aux[pg.aux];
       const uint64_t lo = uint64_t(wi.tile - 1) * kBinTile;
       if (ax.val_pos != 0 && lo < ax.value_bytes)
-        stream_copy(cx, col.values + pg.out_byte + lo, p + ax.val_pos + lo, min(uint64_t(kBinTile), ax.value_bytes - lo));
+        stream_copy(cx, col.values + pg.out_byte + lo, p + ax.val_pos + lo, min(uint64_t(kBinTile), ax.value_bytes - lo), true);
     } else if (wi.tile == 0 || wi.tile == 0xffffffffu) {
       PageAux *ax = pg.aux != 0xffffffffu ? aux + pg.aux : nullptr;
       uint32_t vb = 0;
@@ -479,6 +479,14 @@ void sb_release_columns(sb_ctx *ctx, sb_column_out *outs, uint64_t n) {
   }
 }
 
+// value-byte tiles of an unstaged binary page: a plain (codec None) page holds (n + 1) offsets before its
+// value bytes, so at most length - (n + 1) * OW of them
+static uint64_t bin_value_tiles(const sb_page_meta &m, uint64_t OW) {
+  const uint64_t off_bytes = (m.num_values + 1) * OW;
+  const uint64_t vmax = m.length > off_bytes ? m.length - off_bytes : 0;
+  return (vmax + kBinTile - 1) / kBinTile;
+}
+
 int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, int32_t out_mem, sb_column_out *outs) {
   if (!ctx) return SB_CUDA;
   if (!cols || !outs || (out_mem != SB_MEM_HOST && out_mem != SB_MEM_DEVICE)) return fail(ctx, SB_INVALID_ARG, "bad arguments");
@@ -521,7 +529,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       } else {
         uint64_t out_bytes = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * W;
         bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type) && !col_nested(ci);
-        if (col_binary(ci) && !col_nested(ci)) n_items += 1 + (m.length + kBinTile - 1) / kBinTile; // tile 0 + value slices
+        if (col_binary(ci) && !col_nested(ci)) n_items += 1 + bin_value_tiles(m, W); // tile 0 + value slices
         else n_items += tiled ? std::max<uint64_t>(1, (out_bytes + kTileBytes - 1) / kTileBytes) : 1;
       }
       if (plan) n_plan += 1;
@@ -683,7 +691,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
         uint64_t out_b = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * uint64_t(std::max(1, W));
         bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type) && !nested;
         uint64_t nt = tiled ? std::max<uint64_t>(1, (out_b + kTileBytes - 1) / kTileBytes) : 1;
-        if (binary && !nested) nt = 1 + (m.length + kBinTile - 1) / kBinTile;
+        if (binary && !nested) nt = 1 + bin_value_tiles(m, uint64_t(std::max(1, W)));
         for (uint64_t t = 0; t < nt; ++t) h_items[ii++] = WorkItem{uint32_t(pi), uint32_t(t)};
       }
       src_off += m.length;

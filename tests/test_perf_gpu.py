@@ -145,3 +145,48 @@ def test_config4_nested(ctx):
         cols.append(col)
         record(f"config4 leaf {name} {rows} rows", timed_decode(ctx, [col]))
     record("config4 three leaves, one call", timed_decode(ctx, cols))
+
+
+def test_config4_nested_written_on_gpu(ctx):
+    """the same three leaves, pages written by sb_encode_columns (level streams + leaf value blocks):
+    encode device time, then decode of those pages; the oracle reads the first pages to the same arrays"""
+    nested = [(sbo.N_LIST, True), (sbo.N_STRUCT, True), (sbo.N_PRIMITIVE, True)]
+    rng = np.random.default_rng(7)
+    rows = int(os.environ.get("SB_PERF_NESTED_ROWS", 500_000))
+    rep, de, row_start = config4_levels(rng, rows)
+    slots = de >= 2
+    valid = de[slots] == 4
+    ns = int(slots.sum())
+    cols = []
+    for name, t in (("a_i64", sbo.I64), ("b_f64", sbo.F64), ("c_utf8", sbo.BINARY)):
+        if t == sbo.BINARY:
+            lens = np.where(valid, rng.integers(1, 6, ns), 0)
+            off = np.zeros(ns + 1, np.int32)
+            np.cumsum(lens, out=off[1:])
+            vals = (off, rng.integers(97, 123, int(off[-1])).astype(np.uint8))
+        elif t == sbo.F64:
+            vals = rng.integers(0, 1000, ns).astype(np.float64)
+        else:
+            vals = rng.integers(0, 1 << 40, ns).astype(np.int64)
+        arr = sb.LeafArray(t, vals, validity=valid, nullable=True, nested=nested, rep_levels=rep, def_levels=de, rows=rows)
+        best = None
+        for _ in range(3):
+            enc = ctx.encode_columns([arr], sb.write_options(sb.C_LZ4, 2.0, PAGE, seed=42))[0]
+            st = ctx.last_stats()
+            best = st if best is None or st["device_ms"] < best["device_ms"] else best
+        assert [m[1] for m in enc.metas[:-1]] == [int(row_start[r0 + PAGE] - row_start[r0]) for r0 in range(0, rows - PAGE, PAGE)]
+        k = 8
+        nbytes = sum(m[0] for m in enc.metas[:k])
+        ref = oracle_decode_column(t, True, enc.data[:nbytes], enc.metas[:k], nested)
+        dec = ctx.batch_read_array(sb.Column(t, True, enc.data[:nbytes], enc.metas[:k], nested))
+        assert_same_nested(dec, ref, t, nested)
+        n_k = ref["length"]
+        if t != sbo.BINARY:
+            assert np.array_equal(dec.values[valid[:n_k]], vals[:n_k][valid[:n_k]])
+        RESULTS[f"config4 encode leaf {name} {rows} rows (GPU writer)"] = {
+            "pages": best["pages"], "bytes_in": best["bytes_in"], "bytes_out": best["bytes_out"], "device_us": round(best["device_ms"] * 1e3, 1),
+            "encode_gbs": round(best["bytes_in"] / best["device_ms"] / 1e6, 1), "kernel_launches": best["kernel_launches"]}
+        col = sb.Column(t, True, enc.data, enc.metas, nested)
+        cols.append(col)
+        record(f"config4 leaf {name} {rows} rows (GPU-written pages)", timed_decode(ctx, [col]))
+    record("config4 three leaves, one call (GPU-written pages)", timed_decode(ctx, cols))
