@@ -174,6 +174,32 @@ typedef struct {
 int32_t sb_last_stats(const sb_ctx *ctx, sb_stats *out);
 
 /* ------------------------------------------------------------------------------------
+ * PAGE INSPECTOR (host only: walks headers, never touches the device)
+ * ------------------------------------------------------------------------------------ */
+
+/* What stat_body collects for one page (src/stat.rs:36-61,86-152): PageInfo + the codec tree
+ * of the nested sub-pages (Dict -> index page, Freq -> exceptions page of primitive columns). */
+typedef struct {
+  int32_t codec;                   /* top-level Compression id of the value block */
+  uint32_t validity_size;          /* flat nullable leaves: bytes of the validity section after its u32
+                                      length; 0xffffffff otherwise.  (The reference prints the first 4
+                                      bytes of the value block here, src/stat.rs:76 -- not replicated.) */
+  uint32_t levels_size;            /* nested leaves: 12 + rep_len + def_len; 0 otherwise */
+  uint32_t compressed_size;        /* hdr9 */
+  uint32_t uncompressed_size;      /* hdr9 */
+  uint32_t unique_num;             /* Dict: entries in the dictionary; else 0 */
+  uint32_t exceptions_bitmap_size; /* Freq: bytes of the Roaring bitmap; else 0 */
+  int32_t depth;                   /* codecs on the path top -> innermost sub-page */
+  int32_t path[4];                 /* e.g. {Dict, Bitpacking}, {Freq, Lz4}, {Dict, Freq, Bitpacking} */
+} sb_page_info;
+
+/* Replaces stat::stat_simple's per-page body (src/stat.rs:63-152) for one page of a leaf column.
+ * `tree` (optional, NUL-terminated, at most tree_cap bytes) receives the codec tree as text, e.g.
+ * "Dict(Bitpacking)[k=8]".  Errors: SB_IO (truncated page), SB_OUT_OF_SPEC (unknown codec id). */
+int32_t sb_stat_page(const sb_leaf *leaf, const uint8_t *page, uint64_t len, sb_page_info *info,
+                     char *tree, uint64_t tree_cap);
+
+/* ------------------------------------------------------------------------------------
  * ENCODE
  * ------------------------------------------------------------------------------------ */
 

@@ -400,5 +400,18 @@ def _release_encoded(self, encoded):
             r._outs = None
 
 
+def stat_page(type_, nullable, page, nested=None):
+    """stat::stat_simple for one page (src/stat.rs:63-152): (codec tree as text, PageInfo dict).  Host only."""
+    info = _capi.PageInfo()
+    tree = C.create_string_buffer(256)
+    page = bytes(page)
+    rc = _lib.sb_stat_page(C.byref(make_leaf(type_, nullable, nested)), page, len(page), C.byref(info), tree, 256)
+    if rc != _capi.SB_OK:
+        raise StrawboatError(rc, "sb_stat_page")
+    d = {f: getattr(info, f) for f, _ in _capi.PageInfo._fields_ if f != "path"}
+    d["path"] = [info.path[i] for i in range(min(info.depth, 4))]
+    return tree.value.decode(), d
+
+
 Context.encode_columns = _encode_columns
 Context.release_encoded = _release_encoded

@@ -62,6 +62,12 @@ class LeafArray(C.Structure):
                 ("rep_levels", C.c_void_p), ("def_levels", C.c_void_p), ("n_levels", C.c_uint64), ("rows", C.c_uint64)]
 
 
+class PageInfo(C.Structure):
+    _fields_ = [("codec", C.c_int32), ("validity_size", C.c_uint32), ("levels_size", C.c_uint32),
+                ("compressed_size", C.c_uint32), ("uncompressed_size", C.c_uint32), ("unique_num", C.c_uint32),
+                ("exceptions_bitmap_size", C.c_uint32), ("depth", C.c_int32), ("path", C.c_int32 * 4)]
+
+
 class EncodedColumn(C.Structure):
     _fields_ = [("bytes", C.c_void_p), ("nbytes", C.c_uint64), ("metas", C.POINTER(PageMeta)),
                 ("n_pages", C.c_uint64), ("mem", C.c_int32), ("_owner", C.c_void_p)]
@@ -70,7 +76,7 @@ class EncodedColumn(C.Structure):
 # every symbol include/strawboat_b200.h declares
 EXPORTS = ["sb_ctx_create", "sb_ctx_destroy", "sb_ctx_set_stream", "sb_last_error", "sb_version",
            "sb_decode_columns", "sb_decode_pages", "sb_release_columns", "sb_last_stats",
-           "sb_encode_columns", "sb_release_encoded"]
+           "sb_encode_columns", "sb_release_encoded", "sb_stat_page"]
 
 
 def load():
@@ -101,4 +107,6 @@ def load():
     L.sb_encode_columns.restype = C.c_int32
     L.sb_release_encoded.argtypes = [C.c_void_p, C.POINTER(EncodedColumn), C.c_uint64]
     L.sb_release_encoded.restype = None
+    L.sb_stat_page.argtypes = [C.POINTER(Leaf), C.c_char_p, C.c_uint64, C.POINTER(PageInfo), C.c_char_p, C.c_uint64]
+    L.sb_stat_page.restype = C.c_int32
     return L

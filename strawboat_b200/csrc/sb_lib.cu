@@ -459,6 +459,111 @@ int32_t sb_ctx_set_stream(sb_ctx *ctx, void *cuda_stream) {
 
 const char *sb_last_error(const sb_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context (CUDA device unavailable)"; }
 
+// ---- page inspector (src/stat.rs:63-152), host only ------------------------------------
+namespace {
+uint32_t rd_u32(const uint8_t *p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); }
+const char *codec_name(int c) {
+  switch (c) {
+  case SB_C_NONE: return "None";
+  case SB_C_LZ4: return "Lz4";
+  case SB_C_ZSTD: return "Zstd";
+  case SB_C_SNAPPY: return "Snappy";
+  case SB_C_RLE: return "Rle";
+  case SB_C_DICT: return "Dict";
+  case SB_C_ONEVALUE: return "OneValue";
+  case SB_C_FREQ: return "Freq";
+  case SB_C_BITPACK: return "Bitpacking";
+  case SB_C_DELTABP: return "DeltaBitpacking";
+  case SB_C_PATAS: return "Patas";
+  default: return nullptr;
+  }
+}
+// stat_body: one hdr9 + its sub-pages.  `lvl` = position on the path.
+int stat_block(int type, const uint8_t *in, uint64_t len, sb_page_info *info, int lvl, std::string &tree) {
+  if (len < 9) return SB_IO;
+  const int codec = in[0];
+  const char *name = codec_name(codec);
+  if (!name) return SB_OUT_OF_SPEC; // Compression::from_codec (compression/mod.rs:78)
+  const uint32_t compressed = rd_u32(in + 1);
+  if (lvl == 0) {
+    info->codec = codec;
+    info->compressed_size = compressed;
+    info->uncompressed_size = rd_u32(in + 5);
+  }
+  if (lvl < 4) info->path[lvl] = codec;
+  info->depth = lvl + 1;
+  tree += name;
+  const uint8_t *body = in + 9;
+  const uint64_t avail = len - 9;
+  const bool binary = type == SB_BINARY || type == SB_LARGE_BINARY;
+  if (codec == SB_C_DICT) { // stat_dict_body: [index page (u32)][u32 unique_num]
+    if (avail < 9) return SB_IO;
+    const uint64_t sub_len = 9 + uint64_t(rd_u32(body + 1));
+    if (sub_len + 4 > avail) return SB_IO;
+    std::string sub;
+    int rc = stat_block(SB_U32, body, sub_len, info, lvl + 1, sub);
+    if (rc) return rc;
+    const uint32_t k = rd_u32(body + sub_len);
+    if (lvl == 0) info->unique_num = k;
+    tree += "(" + sub + ")[k=" + std::to_string(k) + "]";
+  } else if (codec == SB_C_FREQ) { // stat_freq_body
+    const uint64_t top = binary ? 8 : uint64_t(type_width(type));
+    if (avail < top + 4) return SB_IO;
+    uint64_t p = top;
+    if (binary) {
+      uint64_t l = 0;
+      for (int b = 0; b < 8; ++b) l |= uint64_t(body[b]) << (8 * b);
+      if (l > avail - 12) return SB_IO;
+      p += l;
+    }
+    const uint32_t bm = rd_u32(body + p);
+    if (lvl == 0) info->exceptions_bitmap_size = bm;
+    if (!binary) { // exceptions are a nested page of the same type
+      if (uint64_t(bm) + p + 4 > avail) return SB_IO;
+      std::string sub;
+      int rc = stat_block(type, body + p + 4 + bm, avail - p - 4 - bm, info, lvl + 1, sub);
+      if (rc) return rc;
+      tree += "(" + sub + ")";
+    }
+  }
+  return SB_OK;
+}
+} // namespace
+
+int32_t sb_stat_page(const sb_leaf *leaf, const uint8_t *page, uint64_t len, sb_page_info *info, char *tree, uint64_t tree_cap) {
+  if (!leaf || !info || (len && !page)) return SB_INVALID_ARG;
+  std::memset(info, 0, sizeof(*info));
+  info->validity_size = 0xffffffffu;
+  info->codec = -1;
+  for (int i = 0; i < 4; ++i) info->path[i] = -1;
+  if (tree && tree_cap) tree[0] = 0;
+  if (leaf->type == SB_NULL) return SB_OK; // empty page
+  uint64_t vb = 0;
+  if (leaf->n_nested > 1) { // [u32 rows][u32 rep_len][u32 def_len][rep][def]
+    if (len < 12) return SB_IO;
+    vb = 12 + uint64_t(rd_u32(page + 4)) + rd_u32(page + 8);
+    if (vb > len) return SB_IO;
+    info->levels_size = uint32_t(vb);
+  } else if (leaf->nullable) {
+    if (len < 4) return SB_IO;
+    const uint32_t L = rd_u32(page);
+    if (L > len - 4) return SB_IO;
+    info->validity_size = L;
+    vb = 4 + uint64_t(L);
+  }
+  std::string t;
+  int type = leaf->type;
+  if (type == SB_BOOL) type = SB_U8; // boolean blocks: None / Lz4 / Rle / OneValue, no sub-pages
+  int rc = stat_block(type, page + vb, len - vb, info, 0, t);
+  if (rc) return rc;
+  if (tree && tree_cap) {
+    const size_t n = std::min<size_t>(t.size(), size_t(tree_cap) - 1);
+    std::memcpy(tree, t.data(), n);
+    tree[n] = 0;
+  }
+  return SB_OK;
+}
+
 int32_t sb_last_stats(const sb_ctx *ctx, sb_stats *out) {
   if (!ctx || !out) return SB_INVALID_ARG;
   *out = ctx->stats;
