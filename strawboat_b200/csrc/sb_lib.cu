@@ -133,38 +133,71 @@ __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const Col
   side_flags[i] = 1;
 }
 
-__global__ void __launch_bounds__(64, 16)
-    sb_lz4_kernel(const Lz4Job *__restrict__ jobs, const uint32_t *__restrict__ n_jobs_p, uint32_t n_pages, uint32_t *counter,
-                  int32_t *status, unsigned long long *bytes_done) {
-  __shared__ Lz4Shared sh;
-  __shared__ uint32_t s_job;
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n_big = n_jobs_p[0], n_small = n_jobs_p[1];
+// One CTA = SB_LZ4_PAIRS scanner warps (warps 0..PAIRS-1, one warpgroup) + as many mover warps (the next
+// warpgroup); pair p = warps p and PAIRS + p works on one block at a time.  The mover needs ~120 registers
+// to keep its per-sequence state out of local memory (spills on its critical path cost ~35 % of the block
+// time), the scanner a third of that: the two warpgroups re-split the CTA's register file with setmaxnreg,
+// so 12 blocks stay resident per SM (3 CTAs x 4 pairs) instead of the 8 a uniform 124-register kernel allows.
+constexpr uint32_t SB_LZ4_PAIRS = 4;
+constexpr uint32_t SB_LZ4_CTA = SB_LZ4_PAIRS * 64;
+__device__ __forceinline__ void pair_sync(uint32_t pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+constexpr uint32_t SB_LZ4_SMEM = uint32_t(sizeof(Lz4Shared)) * SB_LZ4_PAIRS + 64;
+
+// job loop of one warp of a pair (ROLE 0 = scanner, 1 = mover).  The two roles are separate code paths
+// from the setmaxnreg on, so ptxas allocates each under its own register limit.
+template <int ROLE>
+__device__ __forceinline__ void lz4_pair_loop(const Lz4Job *__restrict__ jobs, uint32_t n_big, uint32_t n_small, uint32_t n_pages,
+                                              uint32_t *counter, int32_t *status, unsigned long long *bytes_done, Lz4Shared &sh,
+                                              uint32_t *s_job, uint32_t pair) {
+  const uint32_t lane = threadIdx.x & 31;
+  // First job of a pair = its global pair index: the block scheduler deals consecutive CTAs to different
+  // SMs, so the resident blocks spread evenly over the SMs; later jobs come from the ticket counter.
+  bool first = true;
   for (;;) {
-    if (threadIdx.x == 0) {
-      s_job = atomicAdd(counter, 1u);
+    if (ROLE == 0 && lane == 0) {
+      *s_job = first ? blockIdx.x * SB_LZ4_PAIRS + pair : gridDim.x * SB_LZ4_PAIRS + atomicAdd(counter, 1u);
       sh.produced = 0;
       sh.in_ready = 0;
       sh.consumed = 0;
       sh.m_q = 0;
       sh.abort = 0;
     }
-    __syncthreads();
-    const uint32_t j = s_job;
+    pair_sync(pair);
+    const uint32_t j = *s_job;
     if (j >= n_big + n_small) break;
     const Lz4Job job = jobs[j < n_big ? j : n_pages - 1 - (j - n_big)];
     int rc = 0;
     if (job.clen == 0 || job.dlen == 0) {
       // an empty block decodes to nothing; LZ4_decompress_safe rejects everything else here
       if (!(job.dlen == 0 && job.clen == 1 && job.src[0] == 0) && !(job.clen == 0 && job.dlen == 0)) rc = SB_EXTERNAL;
-    } else if (warp == 0) {
+    } else if (ROLE == 0) {
       rc = lz4_scan(job.src, job.clen, &sh);
     } else {
       rc = lz4_move(job.dst, job.dlen, uint32_t(uintptr_t(job.src) & 15) + job.clen, &sh);
     }
     if (rc && lane == 0) atomicCAS(status + job.page, 0, rc);
-    if (threadIdx.x == 0) atomicAdd(bytes_done, (unsigned long long)(job.clen) + job.dlen);
-    __syncthreads();
+    if (ROLE == 0 && lane == 0) atomicAdd(bytes_done, (unsigned long long)(job.clen) + job.dlen);
+    first = false;
+    pair_sync(pair); // both warps are done with the shared state before it is reset
+  }
+}
+
+__global__ void __launch_bounds__(SB_LZ4_CTA, 3)
+    sb_lz4_kernel(const Lz4Job *__restrict__ jobs, const uint32_t *__restrict__ n_jobs_p, uint32_t n_pages, uint32_t *counter,
+                  int32_t *status, unsigned long long *bytes_done) {
+  extern __shared__ __align__(16) uint8_t lz4_dsm[];
+  __shared__ uint32_t s_jobs[SB_LZ4_PAIRS];
+  Lz4Shared *shs = reinterpret_cast<Lz4Shared *>(lz4_dsm);
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t pair = warp % SB_LZ4_PAIRS;
+  const uint32_t n_big = n_jobs_p[0], n_small = n_jobs_p[1];
+  if (warp < SB_LZ4_PAIRS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    lz4_pair_loop<0>(jobs, n_big, n_small, n_pages, counter, status, bytes_done, shs[pair], &s_jobs[pair], pair);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    lz4_pair_loop<1>(jobs, n_big, n_small, n_pages, counter, status, bytes_done, shs[pair], &s_jobs[pair], pair);
   }
 }
 
@@ -921,13 +954,14 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
       if (ctx->lz4_occ == 0) {
         int q = 1;
-        SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, sb_lz4_kernel, 64, 0));
+        SB_TRY_CUDA(cudaFuncSetAttribute(sb_lz4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SB_LZ4_SMEM)));
+        SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, sb_lz4_kernel, SB_LZ4_CTA, SB_LZ4_SMEM));
         ctx->lz4_occ = std::max(1, q);
       }
       const int lz4_occ = ctx->lz4_occ;
-      uint32_t lz4_grid = uint32_t(std::min<uint64_t>(n_pages_total, uint64_t(ctx->sm_count) * std::max(1, lz4_occ)));
+      uint32_t lz4_grid = uint32_t(std::min<uint64_t>((n_pages_total + SB_LZ4_PAIRS - 1) / SB_LZ4_PAIRS, uint64_t(ctx->sm_count) * std::max(1, lz4_occ)));
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_lz0, ctx->aux));
-      sb_lz4_kernel<<<lz4_grid, 64, 0, ctx->aux>>>(d_jobs, d_counters + 2, uint32_t(n_pages_total), d_counters + 1, d_status,
+      sb_lz4_kernel<<<lz4_grid, SB_LZ4_CTA, SB_LZ4_SMEM, ctx->aux>>>(d_jobs, d_counters + 2, uint32_t(n_pages_total), d_counters + 1, d_status,
                                                    reinterpret_cast<unsigned long long *>(d_counters + 38));
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_lz1, ctx->aux));
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));

@@ -266,7 +266,7 @@ struct Lz4Scan {
     return any;
   }
   // make stream bytes [.., upto) readable (upto <= total).  false = aborted by the mover.
-  __device__ bool need(uint32_t upto) {
+  __device__ __forceinline__ bool need(uint32_t upto) {
     upto = min(upto, total);
     while (ready < upto) {
       if (issued > ready) {
@@ -287,7 +287,7 @@ struct Lz4Scan {
   // room for `n` more entries.  Once the queue is full the scanner stays away until the mover has
   // retired `slack` more entries: it then scans that many sequences in one go instead of paying the
   // housekeeping (publish / refresh / poll) once per 32-byte window.
-  __device__ bool room(uint32_t n, uint32_t slack = 0) {
+  __device__ __forceinline__ bool room(uint32_t n, uint32_t slack = 0) {
     if (seq + n - c_seen <= SB_LZ4_Q) return true;
     publish();
     while (seq + n + slack - c_seen > SB_LZ4_Q) {
@@ -306,7 +306,7 @@ struct Lz4Scan {
 
 // Returns 0 or SB_EXTERNAL.  The scanner validates the shape of the stream (every token, length
 // byte and offset inside the block); the mover validates offsets and output sizes.
-__device__ int lz4_scan(const uint8_t *src, uint32_t clen, Lz4Shared *sh) {
+__device__ __forceinline__ int lz4_scan(const uint8_t *src, uint32_t clen, Lz4Shared *sh) {
   const uint32_t lane = threadIdx.x & 31;
   constexpr uint32_t IM = SB_LZ4_INR - 1;
   Lz4Scan s;
@@ -478,7 +478,7 @@ struct Lz4Out {
     return __ldcg(dst + sp);
   }
   // whole-warp match copy of `ml` bytes at `mpos` (any length, any overlap)
-  __device__ void match_coop(uint32_t mpos, uint32_t offset, uint32_t ml) {
+  __device__ __forceinline__ void match_coop(uint32_t mpos, uint32_t offset, uint32_t ml) {
     const uint32_t lane = threadIdx.x & 31;
     constexpr uint32_t OM = SB_LZ4_RING - 1;
     for (uint32_t done = 0; done < ml;) {
@@ -614,7 +614,7 @@ __device__ __forceinline__ void lz4_copy16_gs(const uint8_t *s, uint32_t d, uint
   }
 }
 
-__device__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Shared *sh) {
+__device__ __forceinline__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t stream_end, Lz4Shared *sh) {
   const uint32_t lane = threadIdx.x & 31;
   constexpr uint32_t OM = SB_LZ4_RING - 1, IM = SB_LZ4_INR - 1;
   const uint32_t sh_b = smem_u32(sh);
