@@ -30,7 +30,7 @@ struct sb_ctx {
   cudaStream_t stream = nullptr, aux = nullptr;
   bool own_stream = false;
   std::string err;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_cls = nullptr;
   cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr, ev_lz0 = nullptr, ev_lz1 = nullptr; // per-kernel timing
   int sm_count = 0;
   int max_smem_optin = 0;

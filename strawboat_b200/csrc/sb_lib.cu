@@ -438,8 +438,12 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out) {
   sb_ctx *ctx = new (std::nothrow) sb_ctx();
   if (!ctx) return SB_CUDA;
   ctx->device = device;
+  // the side stream carries sb_lz4_kernel, whose blocks must all be resident from the start (each is one
+  // long serial chain): highest priority, so that its CTAs are placed before the main kernel's
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     delete ctx;
     return SB_CUDA;
   }
@@ -449,6 +453,7 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out) {
   for (cudaEvent_t *ev : {&ctx->ev_m0, &ctx->ev_m1, &ctx->ev_lz0, &ctx->ev_lz1}) cudaEventCreate(ev);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_cls, cudaEventDisableTiming);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   // keep freed blocks cached in the stream-ordered pool: steady-state calls do not hit the driver
@@ -474,7 +479,7 @@ void sb_ctx_destroy(sb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
   for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
-  for (cudaEvent_t ev : {ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->ev_join, ctx->ev_m0, ctx->ev_m1, ctx->ev_lz0, ctx->ev_lz1})
+  for (cudaEvent_t ev : {ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->ev_join, ctx->ev_cls, ctx->ev_m0, ctx->ev_m1, ctx->ev_lz0, ctx->ev_lz1})
     if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->aux);
@@ -947,11 +952,16 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   // ---- pass 1 (decode)
   if (n_items) {
     if (any_fixed) {
-      // D0: find top-level LZ4 blocks; run them warp-per-page next to the main kernel
-      sb_classify_kernel<<<uint32_t((n_pages_total + 7) / 8), 256, 0, st>>>(d_pages, d_cols, uint32_t(n_pages_total), d_jobs,
-                                                                              d_counters + 2, d_flags);
+      // D0: find top-level LZ4 blocks; run them next to the main kernel.  The two kernels cannot share an SM
+      // at full occupancy (registers), and the main kernel is persistent: if its CTAs get there first the LZ4
+      // blocks start only when it has finished.  So the side stream (high priority) runs classify and the LZ4
+      // kernel back to back, and the main kernel is released by an event recorded between the two: the LZ4
+      // CTAs are placed first, the main kernel's CTAs fill the SMs as LZ4 blocks retire.
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_fork, st));
       SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+      sb_classify_kernel<<<uint32_t((n_pages_total + 7) / 8), 256, 0, ctx->aux>>>(d_pages, d_cols, uint32_t(n_pages_total), d_jobs,
+                                                                                    d_counters + 2, d_flags);
+      SB_TRY_CUDA(cudaEventRecord(ctx->ev_cls, ctx->aux));
       if (ctx->lz4_occ == 0) {
         int q = 1;
         SB_TRY_CUDA(cudaFuncSetAttribute(sb_lz4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SB_LZ4_SMEM)));
@@ -967,6 +977,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
       ctx->stats.kernel_launches += 2;
     }
+    if (any_fixed) SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_cls, 0));
     SB_TRY_CUDA(cudaEventRecord(ctx->ev_m0, st));
     sb_decode_kernel<<<grid, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items),
                                                 uint32_t(n_items), d_counters, static_cast<uint8_t *>(ctx->d_scratch.p),
