@@ -368,12 +368,28 @@ def main():
                     "gbs": main_bytes / (m_ms * 1e-3) / 1e9 if m_ms > 0 else None},
                    {"kernel": "all kernels of one step (plan upload .. last kernel)", "ms": k_ms, "algorithmic_bytes": int(total_bytes),
                     "gbs": total_bytes / (k_ms * 1e-3) / 1e9}]
-        dom = kernels[0] if l_ms >= m_ms else kernels[1]
+        # sb_lz4_kernel is placed first (high-priority side stream) and holds the SMs for most of the step; the
+        # main kernel's CTAs fill in as LZ4 blocks retire, so its event time includes that wait.  The dominant
+        # kernel is the LZ4 one whenever it spans at least half of the step (same order as the serialised ncu list).
+        kernels[1]["note"] = "event time includes waiting for SMs behind sb_lz4_kernel when LZ4 blocks are present"
+        dom = kernels[0] if (l_ms >= m_ms or l_ms >= 0.5 * k_ms) else kernels[1]
+        # DRAM traffic per launch of that kernel: from the committed `ncu --set full` capture of this same command
+        # (profiles/r1_ncu_full_config2.csv, written by tools/ncu_summary.py); null when the file is absent
+        traffic = None
+        try:
+            import csv
+            rows_ = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_config2.csv"))))
+            col_ = next(i for i, h in enumerate(rows_[0]) if h.startswith(dom["kernel"]))
+            byt = {r[0]: float(r[col_]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[r[1]] for r in rows_ if r[0].startswith("dram__bytes_")}
+            traffic = int(byt["dram__bytes_read.sum"] + byt["dram__bytes_write.sum"]) if rows == 10_000_000 and enc_stats else None
+        except Exception:
+            traffic = None
         line = dict(base, value=world * bytes_out / (ms_per_step * 1e-3) / 1e9, ms_per_step=ms_per_step,
                     gpu_launches=launches, clocks=sampler.result(),
                     roofline={"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
                               "frac": dom["gbs"] / peak, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
-                              "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "kernel_ms": dom["ms"], "traffic": None,
+                              "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "kernel_ms": dom["ms"], "traffic": traffic,
+                              "traffic_source": "profiles/r1_ncu_full_config2.csv (ncu --set full of this command, dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None,
                               "kernels": kernels},
                     host_ms_per_step=host_ms / args.steps)
         if per_column:
