@@ -11,7 +11,7 @@ ctx = sb.Context(0, stream=torch.cuda.current_stream())
 cols, _ = bench.build_workload(rows, 42, ctx) if (len(sys.argv) <= 3 or sys.argv[3] == "ours") else bench.build_workload(rows, 42)
 lib = sb._lib
 out = (C.c_ulonglong * 32)()
-names = ["wait", "load+parse", "scan+validate", "literals", "chain", "far", "rounds", "flush", "publish", "-", "batches", "seqs"]
+names = ["wait", "load+parse", "scan+validate", "literals", "chain", "far", "rounds", "flush", "publish", "periodic_seqs", "batches", "seqs"]
 for c in cols:
     if not c["name"].startswith(which):
         continue
@@ -28,4 +28,4 @@ for c in cols:
     tot = max(1, sum(v[:9]))
     for n, x in zip(names[:9], v[:9]):
         print(f"  {n:14s} {x / nb:9.0f} cyc/batch  {x / ns:7.1f} cyc/seq  {100 * x / tot:5.1f}%")
-    print(f"  total          {tot / nb:9.0f} cyc/batch  {tot / ns:7.1f} cyc/seq")
+    print(f"  total          {tot / nb:9.0f} cyc/batch  {tot / ns:7.1f} cyc/seq   sequences on the periodic path: {v[9]} of {ns}")
