@@ -43,3 +43,27 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "sbo" not in re.findall(r"^\s*(?:import|from)\s+(\w+)", text, flags=re.M), f
                 assert "sb_oracle" not in text and "libsb_oracle" not in text, f
+
+
+def test_ctypes_mirror_matches_the_header(tmp_path):
+    """struct sizes and field offsets of the ctypes mirror == what a C compiler sees in the header"""
+    import subprocess
+    from strawboat_b200 import _capi
+    structs = {"sb_page_meta": _capi.PageMeta, "sb_leaf": _capi.Leaf, "sb_column_in": _capi.ColumnIn, "sb_column_out": _capi.ColumnOut,
+               "sb_stats": _capi.Stats, "sb_write_options": _capi.WriteOptions, "sb_leaf_array": _capi.LeafArray,
+               "sb_encoded_column": _capi.EncodedColumn, "sb_page_info": _capi.PageInfo}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "strawboat_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
