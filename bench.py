@@ -301,18 +301,28 @@ def main():
         # with D2H of another); every byte still crosses the link inside the timed region.
         from concurrent.futures import ThreadPoolExecutor
         n_thr = max(1, min(args.e2e_threads, len(host_cols)))
-        order = sorted(range(len(host_cols)), key=lambda i: -host_cols[i].nbytes)
+        # Columns with the fewest page bytes go first (SB_E2E_STAGGER_US apart): their decoded buffers start
+        # coming back over the link -- the bottleneck of this leg -- while the large inputs are still going up.
+        order = sorted(range(len(host_cols)), key=lambda i: host_cols[i].nbytes)
         groups = [[host_cols[i] for i in order[t::n_thr]] for t in range(n_thr)]
+        stagger = float(os.environ.get("SB_E2E_STAGGER_US", "100")) * 1e-6
         ctxs = [ctx] + [sb.Context(local_rank) for _ in range(n_thr - 1)]
         pool = ThreadPoolExecutor(n_thr)
 
         def one(t):
+            if stagger:
+                t_go = step_t0[0] + t * stagger
+                while time.perf_counter() < t_go:
+                    pass
             out = ctxs[t].decode_columns(groups[t], out="host", copy=False)  # pinned host buffers, zero-copy numpy views
             chk = int(out[0].values[-1])  # touch the result on the host
             out[0].release()
             return chk
 
+        step_t0 = [0.0]
+
         def step_host():
+            step_t0[0] = time.perf_counter()
             return sum(pool.map(one, range(n_thr)))
 
         for _ in range(3):
