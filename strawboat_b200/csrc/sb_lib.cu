@@ -78,7 +78,8 @@ __device__ __forceinline__ bool plain_page(const uint8_t *p, uint32_t len, bool 
   if (len - vb < 9 || p[vb] != SB_C_NONE) return false;
   const uint8_t *h = p + vb;
   uint32_t clen = uint32_t(h[1]) | (uint32_t(h[2]) << 8) | (uint32_t(h[3]) << 16) | (uint32_t(h[4]) << 24);
-  return clen <= len - vb - 9 && uint64_t(clen) == out_bytes && out_bytes >= 4 * SB_RING_CHUNK;
+  // the value bytes are the tail of the page: they start at len - out_bytes whatever the validity section holds
+  return clen == len - vb - 9 && uint64_t(clen) == out_bytes && out_bytes >= 4 * SB_RING_CHUNK;
 }
 
 // side_flags: 0 = decoded by the main kernel, 3 = plain page (codec None): streamed through the TMA ring
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(SB_NT, 4)
     cx.rphase = ring_phase;
 
     const uint8_t *p;
+    uint32_t pending_tma = 0;
     if (staged) {
       const uint32_t mis = uint32_t(uintptr_t(pg.src) & 15);
       const uint32_t bytes = (mis + stage_len + 15) & ~15u;
@@ -275,7 +277,9 @@ __global__ void __launch_bounds__(SB_NT, 4)
         const uint8_t *g = pg.src - mis;
         for (uint32_t o = 0; o < bytes; o += kTmaChunk) tma_load_1d(dsm + o, g + o, min(kTmaChunk, bytes - o), &s_bar);
       }
-      if (bytes) {
+      if (bytes && plain) {
+        pending_tma = bytes; // a plain page streams its value bytes first; the validity section lands meanwhile
+      } else if (bytes) {
         mbar_wait(&s_bar, phase);
         phase ^= 1;
       }
@@ -343,6 +347,14 @@ __global__ void __launch_bounds__(SB_NT, 4)
         n = leaf_len;
       } else if (col.nullable) {
         if (pass == 1) {
+          if (plain) { // header validated by sb_classify_kernel: [validity section][hdr9][n * W value bytes]
+            const uint64_t vbytes = uint64_t(n) * uint32_t(col.W);
+            stream_copy(cx, col.values + out_elem * uint64_t(col.W), pg.src + (pg.len - vbytes), vbytes, true);
+            if (pending_tma) {
+              mbar_wait(&s_bar, phase);
+              phase ^= 1;
+            }
+          }
           vb = decode_validity(cx, p, avail, n, col.validity, pg.out_elem);
         } else { // plan pass: only skip the section
           uint32_t L = avail >= 4 ? ld_u32u(p) : 0xffffffffu;
@@ -375,8 +387,8 @@ __global__ void __launch_bounds__(SB_NT, 4)
           if (stored) {
             const uint32_t dlen = n * uint32_t(col.W);
             stream_copy(cx, col.values + out_elem * uint64_t(col.W), p + vb + 9 + 1 + ((dlen - 15) / 255 + 1), dlen);
-          } else if (plain) { // value bytes stream from global memory behind the staged validity section
-            stream_copy(cx, col.values + out_elem * uint64_t(col.W), pg.src + vb + 9, uint64_t(n) * uint32_t(col.W));
+          } else if (plain) {
+            // value bytes already streamed (before the validity section was decoded)
           } else if (!lz4_side)
             ok = decode_fixed<0>(cx, p + vb, avail - vb, n, col.W, col.is_float != 0,
                                  col.values + out_elem * uint64_t(col.W), &used);
@@ -867,6 +879,8 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   Lz4Job *d_jobs = reinterpret_cast<Lz4Job *>(dT + off_jobs);
   PageAux *d_aux = reinterpret_cast<PageAux *>(dT + off_aux);
   BinEntry *d_entries = static_cast<BinEntry *>(ctx->d_entries.p);
+  static const bool dbg_timing = std::getenv("SB_TIMING") != nullptr; // diagnostic: host phases of the call on stderr
+  const auto t_planned = std::chrono::steady_clock::now();
   if (n_items) {
     SB_TRY(dev_reserve(ctx, ctx->d_scratch, scratch_per_cta * grid));
     SB_TRY_CUDA(cudaMemcpyAsync(dT, hT, tables_bytes, cudaMemcpyHostToDevice, st));
@@ -1023,7 +1037,9 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       bytes_out += (cd.nest_off[d] ? (o.nested_len[d] + 1) * 8 : 0) + (cd.nest_val[d] ? (o.nested_len[d] + 7) / 8 : 0);
   }
   for (void *d : d_inputs) cudaFreeAsync(d, st);
+  const auto t_submitted = std::chrono::steady_clock::now();
   SB_TRY_CUDA(cudaStreamSynchronize(st));
+  const auto t_synced = std::chrono::steady_clock::now();
   if (out_mem == SB_MEM_HOST) { // device copies no longer needed
     for (uint64_t c = 0; c < n_cols; ++c) {
       for (void *p : owners[c]->dev) cudaFreeAsync(p, st);
@@ -1060,6 +1076,11 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     }
   }
   ctx->stats.host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+  if (dbg_timing) {
+    auto ms = [](auto a, auto b) { return std::chrono::duration<float, std::milli>(b - a).count(); };
+    std::fprintf(stderr, "[sb timing] plan %.3f  submit %.3f  wait %.3f  finish %.3f  (device %.3f) ms\n", ms(t_host0, t_planned),
+                 ms(t_planned, t_submitted), ms(t_submitted, t_synced), ms(t_synced, std::chrono::steady_clock::now()), ctx->stats.device_ms);
+  }
   ctx->stats.pages = n_pages_total;
   ctx->stats.bytes_in = bytes_in;
   ctx->stats.bytes_out = bytes_out;
