@@ -78,8 +78,7 @@ __device__ __forceinline__ bool plain_page(const uint8_t *p, uint32_t len, bool 
   if (len - vb < 9 || p[vb] != SB_C_NONE) return false;
   const uint8_t *h = p + vb;
   uint32_t clen = uint32_t(h[1]) | (uint32_t(h[2]) << 8) | (uint32_t(h[3]) << 16) | (uint32_t(h[4]) << 24);
-  // the value bytes are the tail of the page: they start at len - out_bytes whatever the validity section holds
-  return clen == len - vb - 9 && uint64_t(clen) == out_bytes && out_bytes >= 4 * SB_RING_CHUNK;
+  return clen <= len - vb - 9 && uint64_t(clen) == out_bytes && out_bytes >= 4 * SB_RING_CHUNK;
 }
 
 // side_flags: 0 = decoded by the main kernel, 3 = plain page (codec None): streamed through the TMA ring
@@ -267,7 +266,6 @@ __global__ void __launch_bounds__(SB_NT, 4)
     cx.rphase = ring_phase;
 
     const uint8_t *p;
-    uint32_t pending_tma = 0;
     if (staged) {
       const uint32_t mis = uint32_t(uintptr_t(pg.src) & 15);
       const uint32_t bytes = (mis + stage_len + 15) & ~15u;
@@ -277,9 +275,7 @@ __global__ void __launch_bounds__(SB_NT, 4)
         const uint8_t *g = pg.src - mis;
         for (uint32_t o = 0; o < bytes; o += kTmaChunk) tma_load_1d(dsm + o, g + o, min(kTmaChunk, bytes - o), &s_bar);
       }
-      if (bytes && plain) {
-        pending_tma = bytes; // a plain page streams its value bytes first; the validity section lands meanwhile
-      } else if (bytes) {
+      if (bytes) {
         mbar_wait(&s_bar, phase);
         phase ^= 1;
       }
@@ -347,14 +343,6 @@ __global__ void __launch_bounds__(SB_NT, 4)
         n = leaf_len;
       } else if (col.nullable) {
         if (pass == 1) {
-          if (plain) { // header validated by sb_classify_kernel: [validity section][hdr9][n * W value bytes]
-            const uint64_t vbytes = uint64_t(n) * uint32_t(col.W);
-            stream_copy(cx, col.values + out_elem * uint64_t(col.W), pg.src + (pg.len - vbytes), vbytes, true);
-            if (pending_tma) {
-              mbar_wait(&s_bar, phase);
-              phase ^= 1;
-            }
-          }
           vb = decode_validity(cx, p, avail, n, col.validity, pg.out_elem);
         } else { // plan pass: only skip the section
           uint32_t L = avail >= 4 ? ld_u32u(p) : 0xffffffffu;
@@ -387,8 +375,8 @@ __global__ void __launch_bounds__(SB_NT, 4)
           if (stored) {
             const uint32_t dlen = n * uint32_t(col.W);
             stream_copy(cx, col.values + out_elem * uint64_t(col.W), p + vb + 9 + 1 + ((dlen - 15) / 255 + 1), dlen);
-          } else if (plain) {
-            // value bytes already streamed (before the validity section was decoded)
+          } else if (plain) { // value bytes stream from global memory behind the staged validity section
+            stream_copy(cx, col.values + out_elem * uint64_t(col.W), pg.src + vb + 9, uint64_t(n) * uint32_t(col.W));
           } else if (!lz4_side)
             ok = decode_fixed<0>(cx, p + vb, avail - vb, n, col.W, col.is_float != 0,
                                  col.values + out_elem * uint64_t(col.W), &used);
