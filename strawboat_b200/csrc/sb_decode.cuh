@@ -262,19 +262,36 @@ template <bool DELTA> __device__ bool dec_bitpack(Dctx &cx, const uint8_t *src, 
     }
   }
   uint32_t pos = 0;
-  // Uniform width (the rule for Dict indices): every block header sits at b * (1 + 16 * bits0).  All headers are
-  // checked at once (one per thread) and the blocks are unpacked without the serial walk over the headers.
-  if (!DELTA && nblk > 1 && avail > 0) {
+  // Uniform width (the rule for Dict indices, and for sorted values inside one page): every block header sits
+  // at b * (1 + 16 * bits0).  All headers are checked at once (one per thread) and the blocks are handled without
+  // the serial walk over the headers.
+  bool uniform = false;
+  if (nblk > 1 && avail > 0) {
     const uint32_t bits0 = src[0], stride = 1 + 16 * bits0;
     bool same = bits0 <= 32 && uint64_t(nblk) * stride <= avail;
     if (same)
       for (uint32_t b = tid; b < nblk; b += SB_NT) same &= src[b * stride] == bits0;
-    if (__syncthreads_and(same)) {
-      for (uint32_t b = warp; b < nblk; b += SB_NWARP) bp_store(dst, b * 128 + lane * 4, n, bp_unpack_lane(src + b * stride + 1, bits0, lane));
-      cx.ar = mark;
-      return true;
+    uniform = __syncthreads_and(same) != 0;
+    if (uniform) {
+      for (uint32_t b = warp; b < nblk; b += SB_NWARP) {
+        const uint4 v = bp_unpack_lane(src + b * stride + 1, bits0, lane);
+        if (!DELTA) {
+          bp_store(dst, b * 128 + lane * 4, n, v);
+        } else {
+          const uint32_t s = warp_sum(v.x + v.y + v.z + v.w);
+          if (lane == 0) {
+            blk_pos[b] = b * stride;
+            blk_sum[b] = s;
+          }
+        }
+      }
+      if (!DELTA) {
+        cx.ar = mark;
+        return true;
+      }
     }
   }
+  if (!uniform)
   for (uint32_t b = 0; b < nblk; ++b) {
     if (pos >= avail) {
       cx.flag(SB_IO);
