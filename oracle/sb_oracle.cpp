@@ -57,6 +57,19 @@ inline void put_bytes(Bytes &b, const void *p, size_t n) {
   const uint8_t *q = static_cast<const uint8_t *>(p);
   b.insert(b.end(), q, q + n);
 }
+// The reference's decoders are generic over T and push whole values (`output.push(value)` after a reserve);
+// the restatement is byte oriented, so the per-value loops dispatch once on the value width and then move
+// W-byte values with constant-size copies (what the monomorphised Rust loop compiles to).
+template <class F> inline int by_width(int W, F &&f) {
+  switch (W) {
+  case 1: return f(std::integral_constant<size_t, 1>{});
+  case 2: return f(std::integral_constant<size_t, 2>{});
+  case 4: return f(std::integral_constant<size_t, 4>{});
+  case 8: return f(std::integral_constant<size_t, 8>{});
+  case 16: return f(std::integral_constant<size_t, 16>{});
+  default: return f(std::integral_constant<size_t, 32>{});
+  }
+}
 
 struct BitView { // Option<&Bitmap> + slice offset
   const uint8_t *p = nullptr;
@@ -621,7 +634,14 @@ int rle_decompress(const uint8_t *in, size_t in_len, size_t n, int W, Bytes &out
     uint32_t len = load_le<uint32_t>(in + pos);
     const uint8_t *v = in + pos + 4;
     pos += 4 + size_t(W);
-    for (uint32_t k = 0; k < len; ++k) put_bytes(out, v, size_t(W));
+    const size_t at = out.size();
+    out.resize(at + size_t(len) * size_t(W));
+    by_width(W, [&](auto w) {
+      constexpr size_t WW = decltype(w)::value;
+      uint8_t *d = out.data() + at;
+      for (uint32_t k = 0; k < len; ++k) std::memcpy(d + size_t(k) * WW, v, WW);
+      return 0;
+    });
     num += len;
     if (num >= n) break;
   }
@@ -640,7 +660,14 @@ template <class Tr> void onevalue_compress(const typename Tr::V *values, BitView
 }
 int onevalue_decompress(const uint8_t *in, size_t in_len, size_t n, int W, Bytes &out) {
   if (in_len < size_t(W)) return fail(SBO_IO, "one_value: failed to fill whole buffer");
-  for (size_t i = 0; i < n; ++i) put_bytes(out, in, size_t(W));
+  const size_t at = out.size();
+  out.resize(at + n * size_t(W));
+  by_width(W, [&](auto w) {
+    constexpr size_t WW = decltype(w)::value;
+    uint8_t *d = out.data() + at;
+    for (size_t i = 0; i < n; ++i) std::memcpy(d + i * WW, in, WW);
+    return 0;
+  });
   return SBO_OK;
 }
 
@@ -691,12 +718,22 @@ int dict_decompress(const uint8_t *in, size_t in_len, size_t n, int W, Bytes &ou
   if (in_len < data_size) return fail(SBO_OUT_OF_SPEC, "Invalid data size"); // dict.rs:80-86
   size_t k = data_size / size_t(W);
   size_t count = idx_bytes.size() / 4;
-  for (size_t i = 0; i < count; ++i) {
-    uint32_t id = load_le<uint32_t>(idx_bytes.data() + 4 * i);
-    if (id >= k) return fail(SBO_PANIC, "dict: index out of bounds"); // data[*i as usize]
-    put_bytes(out, in + size_t(id) * size_t(W), size_t(W));
-  }
-  return SBO_OK;
+  const size_t at = out.size();
+  out.resize(at + count * size_t(W));
+  return by_width(W, [&](auto w) {
+    constexpr size_t WW = decltype(w)::value;
+    uint8_t *d = out.data() + at;
+    const uint8_t *ib = idx_bytes.data();
+    for (size_t i = 0; i < count; ++i) {
+      uint32_t id = load_le<uint32_t>(ib + 4 * i);
+      if (id >= k) {
+        out.resize(at + i * WW);
+        return fail(SBO_PANIC, "dict: index out of bounds"); // data[*i as usize]
+      }
+      std::memcpy(d + i * WW, in + size_t(id) * WW, WW);
+    }
+    return int(SBO_OK);
+  });
 }
 template <class Tr> double dict_ratio(const Stats<Tr> &s) { // dict.rs:109-120
   if (s.unique_count * 3 >= s.tuple_count) return 0.0;
@@ -749,7 +786,13 @@ template <class Tr> int freq_compress(const Stats<Tr> &s, const sbo_opts &opts, 
 int freq_decompress(const uint8_t *in, size_t in_len, size_t n, int W, bool is_float, Bytes &out) {
   if (in_len < size_t(W) + 4) return fail(SBO_IO, "freq: failed to fill whole buffer");
   size_t begin = out.size();
-  for (size_t i = 0; i < n; ++i) put_bytes(out, in, size_t(W));
+  out.resize(begin + n * size_t(W));
+  by_width(W, [&](auto w) {
+    constexpr size_t WW = decltype(w)::value;
+    uint8_t *d = out.data() + begin;
+    for (size_t i = 0; i < n; ++i) std::memcpy(d + i * WW, in, WW);
+    return 0;
+  });
   size_t bm = load_le<uint32_t>(in + W);
   in += W + 4;
   in_len -= size_t(W) + 4;
@@ -843,6 +886,7 @@ int patas_decompress(const uint8_t *in, size_t in_len, size_t n, int W, Bytes &o
   if (n == 0) return fail(SBO_PANIC, "patas: length - 1 underflow");
   if (in_len < size_t(W)) return fail(SBO_IO, "patas: failed to fill whole buffer");
   size_t begin = out.size();
+  out.reserve(begin + n * size_t(W));
   put_bytes(out, in, size_t(W));
   size_t pos = size_t(W);
   for (size_t i = 1; i < n; ++i) {
@@ -1773,6 +1817,51 @@ int sbo_col_read_page(sbo_col *c, const uint8_t *page, size_t len, uint64_t num_
   c->len += int64_t(n);
   return SBO_OK;
 }
+// batch read of a whole column body (read_integer / read_double / read_binary / read_boolean page loops,
+// src/read/array/integer.rs:210-238): pages back to back, `metas` = (length, num_values) pairs
+int sbo_col_read_pages(sbo_col *c, const uint8_t *body, size_t nbytes, const uint64_t *metas, size_t n_pages) {
+  size_t pos = 0;
+  for (size_t p = 0; p < n_pages; ++p) {
+    const size_t len = size_t(metas[2 * p]);
+    if (len > nbytes - pos) return fail(SBO_IO, "column body shorter than its page lengths");
+    int rc = sbo_col_read_page(c, body + pos, len, metas[2 * p + 1]);
+    if (rc) return rc;
+    pos += len;
+  }
+  return SBO_OK;
+}
+
+// page loop of NativeWriter::encode_chunk for one flat leaf (write/common.rs:71-115): pages of `page_rows`
+// rows appended to `out`; metas_out receives (length, num_values) per page; page p samples with seed + p
+int sbo_write_column(const sbo_leaf *leaf, const sbo_array *arr, const sbo_opts *opts, uint64_t page_rows, sbo_buf *out,
+                     uint64_t *metas_out, size_t metas_cap, size_t *n_pages_out) {
+  if (leaf->type == SBO_BINARY || leaf->type == SBO_LARGE_BINARY || leaf->type == SBO_BOOL || leaf->type == SBO_NULL)
+    return fail(SBO_NYI, "sbo_write_column: fixed-width leaves only (the python loop covers the others)");
+  const size_t n = size_t(arr->n), W = size_t(type_width(leaf->type));
+  const size_t pr = page_rows ? size_t(std::min<uint64_t>(page_rows, n)) : n;
+  Bytes all;
+  size_t np = 0;
+  for (size_t r = 0; r < n; r += std::max<size_t>(pr, 1), ++np) {
+    if (np >= metas_cap) return fail(SBO_PANIC, "metas_out too small");
+    sbo_array a = *arr;
+    a.values = static_cast<const uint8_t *>(arr->values) + r * W;
+    a.n = int64_t(std::min(pr, n - r));
+    a.validity_offset = arr->validity_offset + int64_t(r);
+    sbo_opts o = *opts;
+    o.seed = opts->seed + np;
+    sbo_buf b{nullptr, 0, 0};
+    int rc = sbo_write_page(leaf, &a, &o, &b);
+    if (rc) return rc;
+    put_bytes(all, b.data, b.len);
+    metas_out[2 * np] = b.len;
+    metas_out[2 * np + 1] = uint64_t(a.n);
+    sbo_buf_free(&b);
+  }
+  *n_pages_out = np;
+  export_buf(all, out);
+  return SBO_OK;
+}
+
 int64_t sbo_col_len(const sbo_col *c) { return c->len; }
 const uint8_t *sbo_col_values(const sbo_col *c, size_t *nbytes) {
   if (c->leaf.type == SBO_BOOL) {

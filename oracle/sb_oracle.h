@@ -135,6 +135,11 @@ sbo_col *sbo_col_new(const sbo_leaf *leaf);
 void sbo_col_free(sbo_col *c);
 /* One iteration of the page loop of read_* (read_validity + decompress_*). */
 int sbo_col_read_page(sbo_col *c, const uint8_t *page, size_t len, uint64_t num_values);
+/* whole column body, page loop inside the library (metas = (length, num_values) pairs) */
+int sbo_col_read_pages(sbo_col *c, const uint8_t *body, size_t nbytes, const uint64_t *metas, size_t n_pages);
+/* page loop of encode_chunk for one fixed-width flat leaf */
+int sbo_write_column(const sbo_leaf *leaf, const sbo_array *arr, const sbo_opts *opts, uint64_t page_rows, sbo_buf *out,
+                     uint64_t *metas_out, size_t metas_cap, size_t *n_pages_out);
 int64_t sbo_col_len(const sbo_col *c);
 const uint8_t *sbo_col_values(const sbo_col *c, size_t *nbytes);
 const uint8_t *sbo_col_offsets(const sbo_col *c, size_t *nbytes);

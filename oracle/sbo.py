@@ -46,9 +46,30 @@ class Buf(C.Structure):
     _fields_ = [("data", C.POINTER(C.c_uint8)), ("len", C.c_size_t), ("cap", C.c_size_t)]
 
 
+def _host_arch():
+    """identity of this host's CPU (model + ISA flags): the library is built -march=native"""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        keep = [ln for ln in txt.splitlines() if ln.startswith(("model name", "flags"))][:2]
+        return hashlib.sha256("\n".join(keep).encode()).hexdigest()[:16]
+    except OSError:
+        return "unknown"
+
+
+_STAMP = os.path.join(_HERE, ".build_arch")
+
+
 def build(force=False):
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "sb_oracle.cpp")):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    stale = not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "sb_oracle.cpp"))
+    try:
+        other_cpu = open(_STAMP).read().strip() != _host_arch()
+    except OSError:
+        other_cpu = True
+    if force or stale or other_cpu:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+        with open(_STAMP, "w") as f:
+            f.write(_host_arch())
     return _SO
 
 
@@ -58,13 +79,14 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()  # no-op when the library is current and was built on this CPU model
         L = C.CDLL(_SO)
         L.sbo_last_error.restype = C.c_char_p
         L.sbo_col_new.restype = C.c_void_p
         L.sbo_col_free.argtypes = [C.c_void_p]
         L.sbo_col_read_page.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]
+        L.sbo_col_read_pages.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.sbo_write_column.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.sbo_col_len.argtypes = [C.c_void_p]
         L.sbo_col_len.restype = C.c_int64
         for f in ("sbo_col_values", "sbo_col_offsets", "sbo_col_validity"):
@@ -238,6 +260,67 @@ def read_column(leaf, pages):
         return out
     finally:
         L.sbo_col_free(col)
+
+
+def read_column_body(leaf, body, metas, fetch=True):
+    """batch read of a whole column body with the page loop inside the library (no per-page Python work: this
+    is the form the CPU baseline times).  body: bytes / uint8 ndarray; metas: [(length, num_values)].
+    fetch=False returns only the length (the decoded buffers stay inside the library and are freed)."""
+    L = lib()
+    if not isinstance(leaf, Leaf):
+        leaf = make_leaf(*leaf)
+    buf = np.frombuffer(body, dtype=np.uint8) if isinstance(body, (bytes, bytearray, memoryview)) else np.ascontiguousarray(body, dtype=np.uint8)
+    m = np.ascontiguousarray(np.array(metas, dtype=np.uint64).reshape(-1, 2))
+    col = L.sbo_col_new(C.byref(leaf))
+    try:
+        _check(L.sbo_col_read_pages(col, buf.ctypes.data if buf.size else None, buf.size, m.ctypes.data, len(m)))
+        out = {"length": L.sbo_col_len(col)}
+        if not fetch:
+            return out
+        n = C.c_size_t()
+        p = L.sbo_col_values(col, C.byref(n))
+        raw = np.ctypeslib.as_array((C.c_uint8 * n.value).from_address(p)).copy() if n.value else np.zeros(0, np.uint8)
+        t = leaf.type
+        out["values"] = raw.view(NP_OF[t]) if t in NP_OF else raw
+        if t in (BINARY, LARGE_BINARY):
+            p = L.sbo_col_offsets(col, C.byref(n))
+            o = np.ctypeslib.as_array((C.c_uint8 * n.value).from_address(p)).copy()
+            out["offsets"] = o.view(np.int64 if t == LARGE_BINARY else np.int32)
+        p = L.sbo_col_validity(col, C.byref(n))
+        out["validity"] = None
+        if p:
+            out["validity"] = np.ctypeslib.as_array((C.c_uint8 * ((n.value + 7) // 8)).from_address(p)).copy() if n.value else np.zeros(0, np.uint8)
+            out["validity_len"] = n.value
+        if leaf.n_nested > 1:
+            nd = L.sbo_col_nested_depths(col)
+            out["nested"] = []
+            for d in range(nd):
+                p = L.sbo_col_nested_offsets(col, d, C.byref(n))
+                offs = np.frombuffer(C.string_at(p, n.value * 8), dtype=np.int64).copy() if n.value else np.zeros(0, np.int64)
+                p = L.sbo_col_nested_validity(col, d, C.byref(n))
+                val = np.frombuffer(C.string_at(p, (n.value + 7) // 8), dtype=np.uint8).copy() if n.value else np.zeros(0, np.uint8)
+                out["nested"].append({"offsets": offs, "validity": val, "validity_len": n.value})
+        return out
+    finally:
+        L.sbo_col_free(col)
+
+
+def write_column(type_, values, validity=None, nullable=None, opts=None, page_rows=8192):
+    """encode_chunk page loop of one fixed-width flat leaf inside the library: (column body, [(length, num_values)])"""
+    if nullable is None:
+        nullable = validity is not None
+    opts = opts or make_opts()
+    keep = []
+    a = _make_array(type_, values, validity, keep)
+    lf = make_leaf(type_, nullable)
+    n = int(a.n)
+    cap = (n + max(1, page_rows) - 1) // max(1, page_rows) + 1 if page_rows else 2
+    metas = np.zeros((cap, 2), dtype=np.uint64)
+    npg = C.c_size_t()
+    buf = Buf()
+    _check(lib().sbo_write_column(C.byref(lf), C.byref(a), C.byref(opts), page_rows or 0, C.byref(buf), metas.ctypes.data, cap, C.byref(npg)))
+    body = _take(buf)
+    return body, [(int(metas[i, 0]), int(metas[i, 1])) for i in range(npg.value)]
 
 
 def stat_block(type_, block):

@@ -184,8 +184,9 @@ __device__ __forceinline__ bool bin_header(Dctx &cx, const uint8_t *src, uint32_
 // offset; `tab` = this page's slice of the entry table (global).
 // =========================================================================================
 __device__ bool binary_page_size(Dctx &cx, const uint8_t *page, uint32_t page_len, uint32_t vb, uint32_t n, BinEntry *tab,
-                                 uint64_t *out_bytes, uint32_t *val_pos) {
+                                 uint64_t *out_bytes, uint32_t *val_pos, uint32_t *n_ent) {
   *val_pos = 0;
+  *n_ent = 0;
   BinBlock b;
   if (!bin_header(cx, page + vb, page_len - vb, &b)) return false;
   const uint32_t body_pos = vb + 9;
@@ -239,6 +240,7 @@ __device__ bool binary_page_size(Dctx &cx, const uint8_t *page, uint32_t page_le
     uint32_t end;
     uint64_t tot;
     if (!walk_entries(cx, page, page_len, body_pos + used + 4, k, tab, &end, &tot)) return false;
+    *n_ent = k;
     uint64_t sum = 0;
     for (uint32_t i = threadIdx.x; i < n; i += SB_NT) {
       uint32_t id = idx[i];
@@ -291,6 +293,7 @@ __device__ bool binary_page_size(Dctx &cx, const uint8_t *page, uint32_t page_le
       return false;
     }
     if (!walk_entries(cx, page, page_len, body_pos + p, n_vis, tab, &end, &tot)) return false;
+    *n_ent = n_vis;
     *out_bytes = tot + top_len * uint64_t(n - n_vis);
     cx.ar = mark;
     return true;
@@ -306,7 +309,7 @@ __device__ bool binary_page_size(Dctx &cx, const uint8_t *page, uint32_t page_le
 // chunks of SB_NT * RPT with a block scan of the row lengths.
 template <int OW, class RowSrc>
 __device__ void emit_rows(Dctx &cx, uint32_t n, RowSrc &rs, typename OffT<OW>::T *out_off /* &offsets[elem] */,
-                          uint8_t *out_val /* values + page base */, uint64_t base, bool first) {
+                          uint8_t *out_val /* values + page base */, uint64_t base, bool first, uint64_t limit /* value bytes the plan pass sized */) {
   using O = typename OffT<OW>::T;
   constexpr uint32_t RPT = 4, CH = SB_NT * RPT;
   const uint32_t tid = threadIdx.x;
@@ -330,7 +333,11 @@ __device__ void emit_rows(Dctx &cx, uint32_t n, RowSrc &rs, typename OffT<OW>::T
     for (uint32_t j = 0; j < RPT; ++j) {
       const uint8_t *s = ptrs[j];
       uint8_t *d = out_val + pre;
-      for (uint32_t i = 0; i < lens[j]; ++i) d[i] = s[i];
+      if (pre + lens[j] <= limit) {
+        for (uint32_t i = 0; i < lens[j]; ++i) d[i] = s[i];
+      } else {
+        cx.flag(SB_PANIC); // the page changed between the two passes / inconsistent exception ranks: never write past the plan
+      }
       pre += lens[j];
       offs[j] = O(base + pre);
     }
@@ -360,9 +367,15 @@ struct RowsFreq {
   const uint8_t *page;
   const uint8_t *top;
   uint32_t top_len;
+  uint32_t n_ent; // entries the plan pass recorded (ranks beyond it: duplicate / unsorted bitmap values)
+  int *err;
   __device__ __forceinline__ void get(uint32_t r, const uint8_t **p, uint32_t *l) const {
     uint32_t k = rank[r];
-    if (k) {
+    if (k > n_ent) {
+      atomicCAS(err, 0, int(SB_PANIC));
+      *p = top;
+      *l = 0;
+    } else if (k) {
       uint2 e = *reinterpret_cast<const uint2 *>(tab + (k - 1));
       *p = page + e.x;
       *l = e.y;
@@ -397,7 +410,7 @@ __device__ __forceinline__ const BinEntry *stage_entries(Dctx &cx, const BinEntr
 template <int OW>
 __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, uint32_t vb, uint32_t n,
                               typename OffT<OW>::T *out_off, uint8_t *out_val, uint64_t base, bool first,
-                              const BinEntry *tab, bool values_tiled) {
+                              const BinEntry *tab, bool values_tiled, uint32_t n_ent, uint64_t limit) {
   using O = typename OffT<OW>::T;
   BinBlock b;
   if (!bin_header(cx, page + vb, page_len - vb, &b)) return false;
@@ -462,6 +475,10 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
       cx.flag(SB_IO);
       return false;
     }
+    if (uint64_t(u2) != limit) { // the size the plan pass reserved for this page
+      cx.flag(SB_PANIC);
+      return false;
+    }
     if (values_tiled && b.codec == SB_C_NONE && c2 == u2) return true; // value bytes: tiles 1.. of this page
     return dec_basic(cx, b.codec, h2 + 9, c2, out_val, u2);
   }
@@ -478,7 +495,7 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
       return false;
     }
     RowsConst rs{b.body + 4, len};
-    emit_rows<OW>(cx, n, rs, out_off, out_val, base, first);
+    emit_rows<OW>(cx, n, rs, out_off, out_val, base, first, limit);
     return true;
   }
   case SB_C_DICT: {
@@ -495,10 +512,14 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
       return false;
     }
     uint32_t k = ld_u32u(b.body + used);
+    if (k != n_ent) { // not the dictionary the plan pass walked
+      cx.flag(SB_PANIC);
+      return false;
+    }
     tab = stage_entries(cx, tab, k);
     __syncthreads();
     RowsDict rs{idx, tab, page, k};
-    emit_rows<OW>(cx, n, rs, out_off, out_val, base, first);
+    emit_rows<OW>(cx, n, rs, out_off, out_val, base, first, limit);
     __syncthreads();
     cx.ar = mark;
     return true;
@@ -534,10 +555,10 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
     __syncthreads();
     // exception e is the e-th VISITED exception row: ranks of rows < n are dense because
     // the bitmap is sorted, except for (malformed) rows >= n which the size pass ignored too
-    tab = stage_entries(cx, tab, n); // at most one exception per row
+    tab = stage_entries(cx, tab, n_ent); // the entries the plan pass recorded (at most one per row)
     __syncthreads();
-    RowsFreq rs{rank, tab, page, b.body + 8, uint32_t(top_len)};
-    emit_rows<OW>(cx, n, rs, out_off, out_val, base, first);
+    RowsFreq rs{rank, tab, page, b.body + 8, uint32_t(top_len), n_ent, cx.err};
+    emit_rows<OW>(cx, n, rs, out_off, out_val, base, first, limit);
     __syncthreads();
     cx.ar = mark;
     return true;

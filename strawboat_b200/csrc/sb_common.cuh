@@ -38,6 +38,8 @@ struct PageDesc {
 struct PageAux {
   uint64_t value_bytes;
   uint32_t val_pos; // binary Basic / None pages: page position of the plain value bytes (0 = not tileable)
+  uint32_t n_ent;   // binary Dict / Freq pages: BinEntry records the plan pass wrote for this page
+  uint32_t failed;  // plan pass rejected the page (status holds the reason): pass 1 must not touch it
   uint32_t pad;
   uint32_t cnt[SB_MAX_NESTED];
   uint64_t base[SB_MAX_NESTED];

@@ -923,7 +923,15 @@ __device__ uint32_t decode_validity(Dctx &cx, const uint8_t *src, uint32_t avail
     cx.flag(SB_IO);
     return 0xffffffffu;
   }
-  if (L == 0) return 4;
+  if (L == 0) {
+    // the reference pushes nothing (read_basic.rs:43-45) and the array constructor then rejects the validity
+    // length (PrimitiveArray::try_new -> OutOfSpec): a page with rows but no bitmap is an error, not all-null
+    if (n) {
+      cx.flag(SB_OUT_OF_SPEC);
+      return 0xffffffffu;
+    }
+    return 4;
+  }
   // one bit-packed hybrid-RLE run (parquet2 encode_bool); RLE runs are `unreachable!()` upstream
   const uint8_t *p = src + 4;
   uint64_t header = 0;

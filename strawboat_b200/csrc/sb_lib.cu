@@ -357,15 +357,20 @@ __global__ void __launch_bounds__(SB_NT, 4)
       if (ok && pass == 0) {
         if (is_binary_type(col.type)) {
           uint64_t vbytes = 0;
-          uint32_t val_pos = 0;
-          ok = binary_page_size(cx, p, avail, vb, n, entries + pg.tab_off, &vbytes, &val_pos);
+          uint32_t val_pos = 0, n_ent = 0;
+          ok = binary_page_size(cx, p, avail, vb, n, entries + pg.tab_off, &vbytes, &val_pos, &n_ent);
+          ok = !__syncthreads_or(!ok || *cx.err != 0); // per-thread flags (bad dictionary index, ...) count too
           if (tid == 0) {
             ax->value_bytes = ok ? vbytes : 0;
             ax->val_pos = ok ? val_pos : 0;
+            ax->n_ent = ok ? n_ent : 0;
+            ax->failed = ok ? 0u : 1u;
           }
         } else if (tid == 0) {
           ax->value_bytes = 0;
         }
+      } else if (ok && pass == 1 && ax && ax->failed) {
+        // rejected by the plan pass (status already holds the reason): its outputs were never sized
       } else if (ok) {
         if (col.type == SB_BOOL) {
           ok = decode_boolean(cx, p + vb, avail - vb, n, col.values, out_elem);
@@ -382,10 +387,12 @@ __global__ void __launch_bounds__(SB_NT, 4)
                                  col.values + out_elem * uint64_t(col.W), &used);
         } else if (col.type == SB_BINARY) {
           ok = decode_binary<4>(cx, p, avail, vb, n, reinterpret_cast<int32_t *>(col.offsets) + out_elem,
-                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off, vtiled);
+                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off, vtiled,
+                                ax->n_ent, ax->value_bytes);
         } else if (col.type == SB_LARGE_BINARY) {
           ok = decode_binary<8>(cx, p, avail, vb, n, reinterpret_cast<int64_t *>(col.offsets) + out_elem,
-                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off, vtiled);
+                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off, vtiled,
+                                ax->n_ent, ax->value_bytes);
         } else {
           cx.flag(SB_NYI);
         }
@@ -534,6 +541,9 @@ int stat_block(int type, const uint8_t *in, uint64_t len, sb_page_info *info, in
   const uint8_t *body = in + 9;
   const uint64_t avail = len - 9;
   const bool binary = type == SB_BINARY || type == SB_LARGE_BINARY;
+  // same nesting cap as the device decoders (dec_dict / dec_freq: at most 3 stacked headers), so a crafted
+  // chain of Dict / Freq headers cannot recurse once per 13 bytes of page
+  if ((codec == SB_C_DICT || codec == SB_C_FREQ) && lvl >= 2) return SB_OUT_OF_SPEC;
   if (codec == SB_C_DICT) { // stat_dict_body: [index page (u32)][u32 unique_num]
     if (avail < 9) return SB_IO;
     const uint64_t sub_len = 9 + uint64_t(rd_u32(body + 1));
@@ -681,7 +691,13 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     }
   }
   std::vector<Owner *> owners(n_cols, nullptr);
+  std::vector<void *> d_inputs; // device copies of host inputs, freed at the end of the call
   auto cleanup = [&]() {
+    // kernels already launched on either stream may still write into the outputs: join before freeing
+    cudaStreamSynchronize(ctx->aux);
+    cudaStreamSynchronize(st);
+    for (void *d : d_inputs) cudaFreeAsync(d, st);
+    d_inputs.clear();
     for (uint64_t c = 0; c < n_cols; ++c) outs[c]._owner = owners[c];
     sb_release_columns(ctx, outs, n_cols);
   };
@@ -741,7 +757,6 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   };
 
   uint64_t pi = 0, ii = 0, i0 = 0, ent = 0, bytes_in = 0, bytes_out = 0;
-  std::vector<void *> d_inputs; // device copies of host inputs, freed at the end of the call
   bool any_fixed = false;
   for (uint64_t c = 0; c < n_cols; ++c) {
     const sb_column_in &ci = cols[c];
@@ -944,6 +959,10 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
         }
       }
       if (binary) {
+        if (ci.leaf.type == SB_BINARY && vbytes > 0x7fffffffull) { // Offsets<i32>::try_push overflows (arrow2): no silent wrap
+          cleanup();
+          return fail(ctx, SB_OUT_OF_SPEC, "column " + std::to_string(c) + ": more than 2 GiB of value bytes do not fit i32 offsets");
+        }
         o.values_bytes = vbytes;
         SB_TRY(dev_out(ow, vbytes, false, &cd.values));
       }

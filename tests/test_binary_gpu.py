@@ -141,3 +141,92 @@ def test_corrupt_binary(ctx):
         bad[1:5] = (0x7fffffff).to_bytes(4, "little")
         res = ctx.decode_columns([sb.Column(sb.BINARY, False, bytes(bad), metas)], raise_on_page_error=False)[0]
         assert res.page_status[0] != 0 and res.page_status[1] == 0
+
+
+def _u32(b, p):
+    return int.from_bytes(b[p:p + 4], "little")
+
+
+def _second_page_intact(ctx, res, data, metas):
+    """page 1 of a two-page column decodes to what the oracle reads from it, whatever happened to page 0"""
+    assert res.page_status[1] == 0
+    l0, n0 = metas[0]
+    ref = oracle_decode_column(sbo.BINARY, False, data[l0:], metas[1:])
+    # a rejected page contributes no value bytes (and its own offsets are undefined): page 1 then starts at byte 0
+    base = int(res.offsets[n0]) if res.page_status[0] == 0 else 0
+    assert np.array_equal(res.offsets[n0 + 1:] - base, ref["offsets"][1:])
+    assert np.array_equal(res.values[base:base + len(ref["values"])], ref["values"])
+
+
+def test_corrupt_dict_entries(ctx):
+    """ADVICE r1 (high): a binary Dict page whose `[u64 len][bytes]` chain is broken fails in the plan pass;
+    the decode pass must not touch it (no reads through a stale entry table, no writes past the sized output)."""
+    rng = np.random.default_rng(16)
+    vals, _ = strings(rng, 4096, 20)
+    data, metas = oracle_encode_column(sbo.BINARY, vals, page_size=2048, opts=sbo.make_opts(force=sbo.C_DICT))
+    # a healthy call first: the context's entry-table pool now holds stale records for the next call
+    ctx.decode_columns([sb.Column(sb.BINARY, False, data, metas)])
+    sub_len = 9 + _u32(data, 9 + 1)  # index sub-page inside the Dict body
+    ent0 = 9 + sub_len + 4           # first `[u64 len]`
+    for new_len in (1 << 40, 0xfffffff0, 3, 0):
+        bad = bytearray(data)
+        bad[ent0:ent0 + 8] = int(new_len).to_bytes(8, "little")
+        res = ctx.decode_columns([sb.Column(sb.BINARY, False, bytes(bad), metas)], raise_on_page_error=False)[0]
+        if new_len > 0xffff:
+            assert res.page_status[0] in (sb._capi.SB_OUT_OF_SPEC, sb._capi.SB_IO)
+        _second_page_intact(ctx, res, data, metas)
+    # the dictionary size itself: larger / smaller than what the index page refers to
+    for k in (1, 5, 1 << 20):
+        bad = bytearray(data)
+        bad[ent0 - 4:ent0] = int(k).to_bytes(4, "little")
+        res = ctx.decode_columns([sb.Column(sb.BINARY, False, bytes(bad), metas)], raise_on_page_error=False)[0]
+        assert res.page_status[0] != 0
+        _second_page_intact(ctx, res, data, metas)
+
+
+def test_corrupt_freq_roaring(ctx):
+    """a binary Freq page whose Roaring array container holds duplicate / unsorted rows: exception ranks no
+    longer match the entries the plan pass walked -- flagged, never read or written out of bounds"""
+    rng = np.random.default_rng(17)
+    n = 4096
+    ids = np.where(rng.random(n) < 0.95, 0, rng.integers(1, 300, n))
+    table = [b"top-value"] + [b"exception-%d" % i for i in range(1, 300)]
+    lens = np.array([len(table[i]) for i in ids])
+    off = np.zeros(n + 1, np.int32)
+    np.cumsum(lens, out=off[1:])
+    dat = np.frombuffer(b"".join(table[i] for i in ids), np.uint8)
+    data, metas = oracle_encode_column(sbo.BINARY, (off, dat), page_size=2048, opts=sbo.make_opts(force=sbo.C_FREQ))
+    top_len = int.from_bytes(data[9:17], "little")
+    rb = 9 + 8 + top_len + 4                      # roaring bytes
+    assert _u32(data, rb) == 12346 and _u32(data, rb + 4) == 1
+    card = int.from_bytes(data[rb + 10:rb + 12], "little") + 1
+    v0 = rb + 8 + 4 + 4                           # first u16 of the array container
+    assert card >= 8
+    cases = []
+    bad = bytearray(data)                         # duplicates
+    bad[v0 + 2:v0 + 4] = bad[v0:v0 + 2]
+    bad[v0 + 6:v0 + 8] = bad[v0 + 4:v0 + 6]
+    cases.append(bad)
+    bad = bytearray(data)                         # unsorted
+    bad[v0:v0 + 2], bad[v0 + 2 * (card - 1):v0 + 2 * card] = bad[v0 + 2 * (card - 1):v0 + 2 * card], bad[v0:v0 + 2]
+    cases.append(bad)
+    bad = bytearray(data)                         # rows beyond the page
+    bad[v0 + 2 * (card - 1):v0 + 2 * card] = (60000).to_bytes(2, "little")
+    cases.append(bad)
+    bad = bytearray(data)                         # cardinality larger than the exception entries that follow
+    bad[rb + 10:rb + 12] = (card + 40 - 1).to_bytes(2, "little")
+    cases.append(bad)
+    for bad in cases:
+        res = ctx.decode_columns([sb.Column(sb.BINARY, False, bytes(bad), metas)], raise_on_page_error=False)[0]
+        _second_page_intact(ctx, res, data, metas)
+
+
+def test_validity_section_without_bitmap(ctx):
+    """`L == 0` pushes no validity (read_basic.rs:43-45) and the array constructor then rejects the
+    page; it must not come back as all-null data with status OK"""
+    v = np.arange(100, dtype=np.int64)
+    page = sbo.write_page(sbo.I64, v, None, nullable=True, opts=sbo.make_opts())
+    L = _u32(page, 0)
+    bad = (0).to_bytes(4, "little") + page[4 + L:]
+    res = ctx.decode_columns([sb.Column(sb.I64, True, bad, [(len(bad), 100)])], raise_on_page_error=False)[0]
+    assert res.page_status[0] == sb._capi.SB_OUT_OF_SPEC

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 import sbo
-from helpers import assert_same, assert_same_nested, oracle_decode_column
+from helpers import assert_same, assert_same_nested
 
 import strawboat_b200 as sb
 
@@ -18,21 +18,12 @@ RESULTS = {}
 PAGE = 8192
 
 
-def dict_strings(rng, n, uniq, null_density, large):
-    """decimal strings of integers(0, uniq) (tests/it/io.rs:385-397), nulls as empty slots"""
-    table = np.zeros((uniq, 4), dtype=np.uint8)
-    tlen = np.zeros(uniq, dtype=np.int64)
-    for i in range(uniq):
-        b = str(i).encode()
-        table[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
-        tlen[i] = len(b)
-    ids = rng.integers(0, uniq, n)
-    validity = rng.random(n) >= null_density
-    lens = np.where(validity, tlen[ids], 0)
-    off = np.zeros(n + 1, dtype=np.int64 if large else np.int32)
-    np.cumsum(lens, out=off[1:])
-    mask = np.arange(4)[None, :] < lens[:, None]
-    return (off, table[ids][mask]), validity
+from strawboat_b200.workloads import config4_levels, dict_strings  # noqa: E402
+
+
+def oracle_column(t, nullable, data, metas, nested=None):
+    """the oracle's batch read of a WHOLE column body (page loop in C++): every page is compared, at BASELINE size"""
+    return sbo.read_column_body(sbo.make_leaf(t, nullable, nested), data, metas)
 
 
 def timed_decode(ctx, cols, reps=5):
@@ -66,20 +57,20 @@ def test_config3_strings(ctx):
     """nullable Utf8 (i32 offsets) + LargeBinary (i64 offsets), uniq = 1000, 40 % nulls, adaptive on:
     pages written by the GPU encoder (Dict with a nested index block), read by the oracle and by us"""
     rng = np.random.default_rng(42)
-    n = int(os.environ.get("SB_PERF_ROWS", 2_000_000))
+    n = int(os.environ.get("SB_PERF_ROWS", 10_000_000))  # BASELINE.json configs[2] size
     cols, total_in = [], 0
     for name, t, large in (("utf8", sb.BINARY, False), ("large_binary", sb.LARGE_BINARY, True)):
         values, validity = dict_strings(rng, n, 1000, 0.4, large)
         enc = ctx.encode_columns([sb.LeafArray(t, values, validity=validity)], sb.write_options(sb.C_LZ4, 2.0, PAGE, seed=42))[0]
         col = sb.Column(t, True, enc.data, enc.metas)
-        # parity on the first 20 pages (the oracle reads what our encoder wrote, we read it too)
-        k = 20
-        nbytes = sum(m[0] for m in enc.metas[:k])
-        ref = oracle_decode_column(t, True, enc.data[:nbytes], enc.metas[:k])
-        dec = ctx.batch_read_array(sb.Column(t, True, enc.data[:nbytes], enc.metas[:k]))
+        # parity on EVERY page: the oracle reads what our encoder wrote, we read it too, both equal the input
+        ref = oracle_column(t, True, enc.data, enc.metas)
+        dec = ctx.batch_read_array(col)
         assert_same(dec, ref, t, True)
-        rows_k = sum(m[1] for m in enc.metas[:k])
-        assert np.array_equal(sbo.unpack_bits(dec.validity, rows_k), validity[:rows_k])
+        assert np.array_equal(sbo.unpack_bits(dec.validity, n), validity)
+        lens = np.diff(dec.offsets.astype(np.int64))
+        assert np.array_equal(lens[validity], np.diff(values[0].astype(np.int64))[validity])
+        del ref, dec
         cols.append(col)
         st = timed_decode(ctx, [col])
         record(f"config3 {name} {n} rows", st)
@@ -87,30 +78,11 @@ def test_config3_strings(ctx):
     record("config3 both columns, one call", st)
 
 
-def config4_levels(rng, rows):
-    """List<Struct<..>> rows: 10 % null lists, lengths integers(0,3), 20 % null structs / leaves
-    (tests/it/io.rs:280-292,399-415).  nested = [(LIST,1),(STRUCT,1),(PRIMITIVE,1)]: max_rep 1, max_def 4"""
-    k = rng.integers(0, 4, rows)
-    null_list = rng.random(rows) < 0.1
-    cnt = np.where(null_list | (k == 0), 1, k)
-    row_of = np.repeat(np.arange(rows), cnt)
-    first = np.ones(len(row_of), dtype=bool)
-    first[1:] = row_of[1:] != row_of[:-1]
-    rep = (~first).astype(np.uint32)
-    de = np.full(len(row_of), 4, dtype=np.uint32)
-    r = rng.random(len(row_of))
-    de[r < 0.2] = 3            # struct valid, leaf null
-    de[r < 0.05] = 2           # null struct
-    de[(k == 0)[row_of]] = 1   # empty list
-    de[null_list[row_of]] = 0  # null list
-    return rep, de, np.cumsum(cnt) - cnt  # entry index of every row
-
-
 def test_config4_nested(ctx):
     """three leaves of List<Struct<a:Int64, b:Float64, c:Utf8>>, each page with its own rep/def streams"""
     nested = [(sbo.N_LIST, True), (sbo.N_STRUCT, True), (sbo.N_PRIMITIVE, True)]
     rng = np.random.default_rng(7)
-    rows = int(os.environ.get("SB_PERF_NESTED_ROWS", 500_000))
+    rows = int(os.environ.get("SB_PERF_NESTED_ROWS", 4_000_000))  # BASELINE.json configs[3] size
     rep, de, row_start = config4_levels(rng, rows)
     cols = []
     for name, t in (("a_i64", sbo.I64), ("b_f64", sbo.F64), ("c_utf8", sbo.BINARY)):
@@ -137,11 +109,10 @@ def test_config4_nested(ctx):
             metas.append((len(pages[-1]), int(e1 - e0)))
         data = b"".join(pages)
         col = sb.Column(t, True, data, metas, nested)
-        k = 8
-        nbytes = sum(m[0] for m in metas[:k])
-        ref = oracle_decode_column(t, True, data[:nbytes], metas[:k], nested)
-        dec = ctx.batch_read_array(sb.Column(t, True, data[:nbytes], metas[:k], nested))
+        ref = oracle_column(t, True, data, metas, nested)  # every page of the leaf
+        dec = ctx.batch_read_array(col)
         assert_same_nested(dec, ref, t, nested)
+        del ref, dec
         cols.append(col)
         record(f"config4 leaf {name} {rows} rows", timed_decode(ctx, [col]))
     record("config4 three leaves, one call", timed_decode(ctx, cols))
@@ -152,7 +123,7 @@ def test_config4_nested_written_on_gpu(ctx):
     encode device time, then decode of those pages; the oracle reads the first pages to the same arrays"""
     nested = [(sbo.N_LIST, True), (sbo.N_STRUCT, True), (sbo.N_PRIMITIVE, True)]
     rng = np.random.default_rng(7)
-    rows = int(os.environ.get("SB_PERF_NESTED_ROWS", 500_000))
+    rows = int(os.environ.get("SB_PERF_NESTED_ROWS", 4_000_000))
     rep, de, row_start = config4_levels(rng, rows)
     slots = de >= 2
     valid = de[slots] == 4
@@ -175,14 +146,13 @@ def test_config4_nested_written_on_gpu(ctx):
             st = ctx.last_stats()
             best = st if best is None or st["device_ms"] < best["device_ms"] else best
         assert [m[1] for m in enc.metas[:-1]] == [int(row_start[r0 + PAGE] - row_start[r0]) for r0 in range(0, rows - PAGE, PAGE)]
-        k = 8
-        nbytes = sum(m[0] for m in enc.metas[:k])
-        ref = oracle_decode_column(t, True, enc.data[:nbytes], enc.metas[:k], nested)
-        dec = ctx.batch_read_array(sb.Column(t, True, enc.data[:nbytes], enc.metas[:k], nested))
+        ref = oracle_column(t, True, enc.data, enc.metas, nested)  # every page: oracle and GPU readers agree ...
+        dec = ctx.batch_read_array(sb.Column(t, True, enc.data, enc.metas, nested))
         assert_same_nested(dec, ref, t, nested)
-        n_k = ref["length"]
-        if t != sbo.BINARY:
-            assert np.array_equal(dec.values[valid[:n_k]], vals[:n_k][valid[:n_k]])
+        assert ref["length"] == ns
+        if t != sbo.BINARY:  # ... and return the input
+            assert np.array_equal(dec.values[valid], vals[valid])
+        del ref, dec
         RESULTS[f"config4 encode leaf {name} {rows} rows (GPU writer)"] = {
             "pages": best["pages"], "bytes_in": best["bytes_in"], "bytes_out": best["bytes_out"], "device_us": round(best["device_ms"] * 1e3, 1),
             "encode_gbs": round(best["bytes_in"] / best["device_ms"] / 1e6, 1), "kernel_launches": best["kernel_launches"]}
