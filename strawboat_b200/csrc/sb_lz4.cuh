@@ -176,7 +176,8 @@ constexpr uint32_t SB_LZ4_Q = 256;          // queue entries (u32 each)
 #endif
 constexpr uint32_t SB_LZ4_NEAR = SB_LZ4_RING - 2048 - 64; // match distance served from the ring
 constexpr uint32_t SB_LZ4_FLUSHQ = 1024;    // write-behind granularity
-constexpr uint32_t SB_LZ4_SMALL = 16;       // literal / match lengths handled one sequence per lane
+constexpr uint32_t SB_LZ4_SMALL = 16;       // match lengths handled one sequence per lane
+constexpr uint32_t SB_LZ4_SMALL_LIT = 32;   // literal runs handled one sequence per lane (two 16-byte passes)
 constexpr uint32_t SB_LZ4_MAXPOS = 0x3fffffffu; // stream / output positions fit 30 bits
 enum { LZ4_E_SEQ = 0u, LZ4_E_END = 1u, LZ4_E_BIG = 2u, LZ4_E_ERROR = 3u }; // entry >> 30
 
@@ -810,7 +811,7 @@ __device__ __forceinline__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t st
         rc = SB_EXTERNAL;
         break;
       }
-      const uint32_t small_mask = __ballot_sync(0xffffffffu, in_seg && lit <= SB_LZ4_SMALL && ml <= SB_LZ4_SMALL);
+      const uint32_t small_mask = __ballot_sync(0xffffffffu, in_seg && lit <= SB_LZ4_SMALL_LIT && ml <= SB_LZ4_SMALL);
       LZ4_T(t4);
       LZ4_ACC(2, t3, t4);
       uint32_t a = i;
@@ -835,8 +836,14 @@ __device__ __forceinline__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t st
         // literals of the whole run at once
         {
           const bool lean = mine && s_lit + lit <= SB_LZ4_INR && d_lit + lit <= SB_LZ4_RING;
-          lz4_copy16_ss(in_b + s_lit, out_b + d_lit, lean ? lit : 0u, __any_sync(0xffffffffu, mine && lit > 4),
+          lz4_copy16_ss(in_b + s_lit, out_b + d_lit, lean ? min(lit, 16u) : 0u, __any_sync(0xffffffffu, mine && lit > 4),
                         __any_sync(0xffffffffu, mine && lit > 8), true);
+          // literal runs of 17-32 bytes (sorted / slowly varying integer columns): a second per-lane pass instead of
+          // moving those sequences one at a time with the whole warp
+          if (__any_sync(0xffffffffu, lean && lit > 16)) {
+            if (lean)
+              for (uint32_t t = 16; t < lit; ++t) sts_u8(out_b + d_lit + t, lds_u8(in_b + s_lit + t)); // no extra live registers
+          }
           if (__any_sync(0xffffffffu, mine && !lean) && mine && !lean) // a ring boundary inside: masked bytes
             for (uint32_t t = 0; t < lit; ++t) sts_u8(out_b + ((op + t) & OM), lds_u8(in_b + ((ls + t) & IM)));
         }
@@ -896,17 +903,35 @@ __device__ __forceinline__ int lz4_move(uint8_t *dst, uint32_t dlen, uint32_t st
           }
           K = lo; // lanes [a, lo) have mpos < s_end: this lane waits until the round start f >= lo
         }
-        uint32_t f = a;
-        while (f < j) {
-          const bool blocked = nearl && lane > f && K > f;
-          const uint32_t dmask = __ballot_sync(0xffffffffu, blocked || lane >= j) & ~((2u << f) - 1u);
-          const uint32_t bnd = dmask ? uint32_t(__ffs(int(dmask))) - 1u : 32u; // first lane not in this round
-          const bool inr = lane >= f && lane < bnd && nearl;
+        // L = first run lane whose match ends after this lane's source begins (mpos + ml is increasing too): the
+        // pending matches this lane may read are exactly the lanes [L, K).  A lane copies as soon as none of them
+        // is pending -- with liblz4-written blocks most near matches read literals or matches that are final, so a
+        // batch takes as many rounds as its dependency DEPTH (2-3), not one per dependent match.
+        uint32_t rmask = 0;
+        {
+          uint32_t lo = a, hi = lane;
+          const uint32_t m_end = mpos + ml;
+#pragma unroll
+          for (int it = 0; it < 5; ++it) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t e_mid = __shfl_sync(0xffffffffu, m_end, mid & 31);
+            if (lo < hi) {
+              if (e_mid <= src) lo = mid + 1;
+              else hi = mid;
+            }
+          }
+          if (K > lo) rmask = ((1u << K) - 1u) & ~((1u << lo) - 1u); // K <= lane <= 31
+        }
+        bool pending = nearl;
+        for (;;) {
+          const uint32_t pend = __ballot_sync(0xffffffffu, pending);
+          if (!pend) break;
+          const bool inr = pending && (pend & rmask) == 0; // the lowest pending lane always qualifies
           lz4_copy16_ss(out_b + s_m2, out_b + d_m, inr && lean ? ml : 0u, gt4, gt8, wide);
           if (any_slow && inr && !lean) // overlap < 4, ring boundary, odd distances
             for (uint32_t t = 0; t < ml; ++t) sts_u8(out_b + ((mpos + t) & OM), o.src_byte(src + t, mpos));
           __syncwarp();
-          f = min(bnd, j);
+          if (inr) pending = false;
         }
         LZ4_T(t9);
         LZ4_ACC(6, t8, t9);
