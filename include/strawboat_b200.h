@@ -51,6 +51,8 @@ enum {
   SB_F64 = 11,
   SB_BINARY = 12,       /* i32 offsets */
   SB_LARGE_BINARY = 13, /* i64 offsets */
+  SB_I128 = 14,         /* PrimitiveType::Int128 (Decimal128 storage): 16-byte little-endian two's complement */
+  SB_I256 = 15,         /* PrimitiveType::Int256 (Decimal256 storage): 32 bytes */
 };
 
 /* ---- codec ids: src/compression/mod.rs:37-108 --------------------------------------- */

@@ -502,6 +502,43 @@ inline sbo_opts default_opts_like(const sbo_opts &o) { // WriteOptions::default(
 // as ordered_float::OrderedFloat (src/compression/double/traits.rs:51-53) unless
 // float_bitwise is set (SURVEY App. C6 deviation used by the GPU encoder).
 // ---------------------------------------------------------------------------------
+// i128 / i256 (arrow2 `i128`, `i256`: src/util/mod.rs:77-78, src/compression/integer/traits.rs:28-39).  Little-endian
+// two's complement; ordered as signed integers; as_i64 keeps the low 64 bits.
+using i128 = __int128;
+struct i256 {
+  unsigned __int128 lo = 0;
+  __int128 hi = 0;
+  bool operator==(const i256 &o) const { return lo == o.lo && hi == o.hi; }
+  bool operator!=(const i256 &o) const { return !(*this == o); }
+  bool operator<(const i256 &o) const { return hi != o.hi ? hi < o.hi : lo < o.lo; }
+  explicit operator int64_t() const { return int64_t(lo); }
+};
+static_assert(sizeof(i128) == 16 && sizeof(i256) == 32, "wide integer layout");
+} // namespace
+namespace std {
+template <> struct hash<::i256> {
+  size_t operator()(const ::i256 &v) const noexcept {
+    uint64_t w[4];
+    std::memcpy(w, &v, 32);
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint64_t x : w) h = (h ^ x) * 0xBF58476D1CE4E5B9ull, h ^= h >> 29;
+    return size_t(h);
+  }
+};
+} // namespace std
+struct I128Hash {
+  size_t operator()(const __int128 &v) const noexcept {
+    uint64_t w[2];
+    std::memcpy(w, &v, 16);
+    uint64_t h = (w[0] ^ 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+    h = (h ^ (h >> 29) ^ w[1]) * 0x94D049BB133111EBull;
+    return size_t(h ^ (h >> 31));
+  }
+};
+namespace {
+template <class K> struct KeyHash { using type = std::hash<K>; };
+template <> struct KeyHash<__int128> { using type = I128Hash; };
+
 template <class T> struct IntTr {
   using V = T;
   using K = T;
@@ -555,7 +592,7 @@ template <class Tr> struct Stats {
   struct Cnt {
     size_t count = 0, first = 0;
   };
-  std::unordered_map<K, Cnt> distinct;
+  std::unordered_map<K, Cnt, typename KeyHash<K>::type> distinct;
   size_t unique_count = 0;
 };
 
@@ -677,7 +714,7 @@ int onevalue_decompress(const uint8_t *in, size_t in_len, size_t n, int W, Bytes
 template <class Tr>
 int dict_compress(const typename Tr::V *values, BitView validity, size_t n, const sbo_opts &opts, Bytes &out) {
   using V = typename Tr::V;
-  std::unordered_map<V, uint32_t> interner;
+  std::unordered_map<V, uint32_t, typename KeyHash<V>::type> interner;
   std::vector<V> sets;
   std::vector<uint32_t> indices;
   indices.reserve(n);
@@ -1542,6 +1579,8 @@ int type_width(int t) {
   case SBO_I64:
   case SBO_U64:
   case SBO_F64: return 8;
+  case SBO_I128: return 16;
+  case SBO_I256: return 32;
   }
   return 0;
 }
@@ -1683,6 +1722,8 @@ int compress_values(int type, const sbo_array *a, const sbo_opts *o, Bytes &out)
   case SBO_U64: return compress_typed<IntTr<uint64_t>>(a, o, out);
   case SBO_F32: return compress_typed<FloatTr<float, uint32_t>>(a, o, out);
   case SBO_F64: return compress_typed<FloatTr<double, uint64_t>>(a, o, out);
+  case SBO_I128: return compress_typed<IntTr<i128>>(a, o, out);
+  case SBO_I256: return compress_typed<IntTr<i256>>(a, o, out);
   case SBO_BOOL:
     return compress_boolean(BitView{static_cast<const uint8_t *>(a->values), a->values_bit_offset},
                             BitView{a->validity, a->validity_offset}, size_t(a->n), *o, out);

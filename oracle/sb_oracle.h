@@ -48,6 +48,8 @@ enum {
   SBO_F64 = 11,
   SBO_BINARY = 12,       /* i32 offsets */
   SBO_LARGE_BINARY = 13, /* i64 offsets */
+  SBO_I128 = 14,         /* Decimal128 storage */
+  SBO_I256 = 15,         /* Decimal256 storage */
 };
 
 /* Codec ids, src/compression/mod.rs:37-108 */

@@ -14,14 +14,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libsb_oracle.so")
 
 # physical types (same numbering as include/strawboat_b200.h)
-NULL, BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F32, F64, BINARY, LARGE_BINARY = range(14)
+NULL, BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F32, F64, BINARY, LARGE_BINARY, I128, I256 = range(16)
 # codecs
 C_NONE, C_LZ4, C_ZSTD, C_SNAPPY = 0, 1, 2, 3
 C_RLE, C_DICT, C_ONEVALUE, C_FREQ, C_BITPACK, C_DELTABP, C_PATAS = 10, 11, 12, 13, 14, 15, 16
 N_PRIMITIVE, N_LIST, N_STRUCT = 0, 1, 2
 
 NP_OF = {I8: np.int8, I16: np.int16, I32: np.int32, I64: np.int64, U8: np.uint8, U16: np.uint16,
-         U32: np.uint32, U64: np.uint64, F32: np.float32, F64: np.float64}
+         U32: np.uint32, U64: np.uint64, F32: np.float32, F64: np.float64,
+         I128: np.dtype("V16"), I256: np.dtype("V32")}
 WIDTH = {t: np.dtype(d).itemsize for t, d in NP_OF.items()}
 
 

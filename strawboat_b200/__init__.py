@@ -17,13 +17,14 @@ import numpy as np
 
 from . import _capi
 from ._capi import (BINARY, BOOL, C_BITPACK, C_DELTABP, C_DICT, C_FREQ, C_LZ4, C_NONE, C_ONEVALUE, C_PATAS,  # noqa: F401
-                    C_RLE, C_SNAPPY, C_ZSTD, F32, F64, I8, I16, I32, I64, LARGE_BINARY, MEM_DEVICE, MEM_HOST,
+                    C_RLE, C_SNAPPY, C_ZSTD, F32, F64, I8, I16, I32, I64, I128, I256, LARGE_BINARY, MEM_DEVICE, MEM_HOST,
                     N_LIST, N_PRIMITIVE, N_STRUCT, NULL, STATUS_NAMES, U8, U16, U32, U64)
 
 _lib = _capi.load()  # raises ImportError if the CUDA library has not been built
 
 NP_OF = {I8: np.int8, I16: np.int16, I32: np.int32, I64: np.int64, U8: np.uint8, U16: np.uint16,
-         U32: np.uint32, U64: np.uint64, F32: np.float32, F64: np.float64}
+         U32: np.uint32, U64: np.uint64, F32: np.float32, F64: np.float64,
+         I128: np.dtype("V16"), I256: np.dtype("V32")}  # Decimal128 / Decimal256 storage: opaque 16 / 32-byte little-endian values
 
 
 class StrawboatError(RuntimeError):

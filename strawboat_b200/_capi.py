@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libstrawboat_b200.so")
 SB_OK, SB_OUT_OF_SPEC, SB_IO, SB_EXTERNAL, SB_NYI, SB_CUDA, SB_INVALID_ARG, SB_PANIC = range(8)
 STATUS_NAMES = ["SB_OK", "SB_OUT_OF_SPEC", "SB_IO", "SB_EXTERNAL", "SB_NYI", "SB_CUDA", "SB_INVALID_ARG", "SB_PANIC"]
 
-NULL, BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F32, F64, BINARY, LARGE_BINARY = range(14)
+NULL, BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F32, F64, BINARY, LARGE_BINARY, I128, I256 = range(16)
 C_NONE, C_LZ4, C_ZSTD, C_SNAPPY = 0, 1, 2, 3
 C_RLE, C_DICT, C_ONEVALUE, C_FREQ, C_BITPACK, C_DELTABP, C_PATAS = 10, 11, 12, 13, 14, 15, 16
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -171,12 +171,23 @@ template <> struct Elem<1> { using T = uint8_t; };
 template <> struct Elem<2> { using T = uint16_t; };
 template <> struct Elem<4> { using T = uint32_t; };
 template <> struct Elem<8> { using T = uint64_t; };
+// i128 / i256 (Decimal128 / Decimal256 storage, src/util/mod.rs:77-78): moved as 16-byte vectors, never interpreted
+struct __align__(16) U128 {
+  uint4 v;
+};
+struct __align__(16) U256 {
+  uint4 lo, hi;
+};
+template <> struct Elem<16> { using T = U128; };
+template <> struct Elem<32> { using T = U256; };
 
 template <int W> __device__ __forceinline__ typename Elem<W>::T ld_elem_u(const uint8_t *p) {
   if constexpr (W == 1) return uint8_t(*p);
   else if constexpr (W == 2) return uint16_t(ld_u16u(p));
   else if constexpr (W == 4) return ld_u32u(p);
-  else return ld_u64u(p);
+  else if constexpr (W == 8) return ld_u64u(p);
+  else if constexpr (W == 16) return U128{ld_u128u(p)};
+  else return U256{ld_u128u(p), ld_u128u(p + 16)};
 }
 
 // ------------------------------------------------------------------------------------

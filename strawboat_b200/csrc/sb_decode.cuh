@@ -21,10 +21,17 @@ namespace sb {
 // ------------------------------------------------------------------------------------
 template <int W, class Gen> __device__ __forceinline__ void emit(uint8_t *dst, uint32_t lo, uint32_t hi, Gen &g) {
   using T = typename Elem<W>::T;
-  constexpr uint32_t E = 16 / W;
   const uint32_t tid = threadIdx.x;
   if (hi <= lo) return;
   T *out = reinterpret_cast<T *>(dst);
+  if constexpr (W >= 16) { // one element = one or two 16-byte vectors; dst is 16-byte aligned (column buffer / arena)
+    for (uint32_t i = lo + tid; i < hi; i += SB_NT) {
+      g.seek(i);
+      out[i] = g.next();
+    }
+    return;
+  }
+  constexpr uint32_t E = W >= 16 ? 1 : 16 / W;
   uint32_t mis = uint32_t((16 - ((uintptr_t(dst) + uint64_t(lo) * W) & 15)) & 15) / W;
   uint32_t head_end = min(hi, lo + mis);
   for (uint32_t i = lo + tid; i < head_end; i += SB_NT) {
@@ -538,7 +545,7 @@ __device__ bool dec_dict(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t 
     g.k = k;
     g.err = cx.err;
     g.tab = table;
-    g.aligned = (uintptr_t(table) & (W - 1)) == 0;
+    g.aligned = (uintptr_t(table) & ((W > 16 ? 16 : W) - 1)) == 0;
     if (!g.aligned) {
       uint8_t *tab = static_cast<uint8_t *>(cx.ar.alloc_shared(uint64_t(k) * W));
       if (tab) {
@@ -723,6 +730,8 @@ __device__ bool decode_fixed(Dctx &cx, const uint8_t *src, uint32_t avail, uint3
   case 1: return decode_fixed_w<LEVEL, 1>(cx, codec, body, compressed, body_avail, n, is_float, dst);
   case 2: return decode_fixed_w<LEVEL, 2>(cx, codec, body, compressed, body_avail, n, is_float, dst);
   case 4: return decode_fixed_w<LEVEL, 4>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  case 16: return decode_fixed_w<LEVEL, 16>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  case 32: return decode_fixed_w<LEVEL, 32>(cx, codec, body, compressed, body_avail, n, is_float, dst);
   default: return decode_fixed_w<LEVEL, 8>(cx, codec, body, compressed, body_avail, n, is_float, dst);
   }
 }

@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(SB_NT)
       } else if (col.type == SB_BINARY || col.type == SB_LARGE_BINARY) {
         used = enc_binary(cx, BinView{col.values, col.offsets + pg.row0 * uint64_t(col.W), col.W}, valid, n, col.values_bytes, o,
                           out + pos);
+      } else if (col.W >= 16) { // i128 / i256
+        used = enc_wide<0>(cx, col.values + pg.row0 * uint64_t(col.W), col.W, valid, n, o, out + pos);
       } else {
         used = enc_fixed<0>(cx, Vals{col.values + pg.row0 * uint64_t(col.W), col.W}, col.tclass, valid, n, o, out + pos);
       }
@@ -380,7 +382,7 @@ int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_col
   uint64_t n_lv_blocks = 0, n_lv_pages = 0;
   for (uint64_t c = 0; c < n_cols; ++c) {
     const sb_leaf_array &a = cols[c];
-    if (a.leaf.type < SB_NULL || a.leaf.type > SB_LARGE_BINARY) return fail(ctx, SB_NYI, "unsupported physical type");
+    if (a.leaf.type < SB_NULL || a.leaf.type > SB_I256) return fail(ctx, SB_NYI, "unsupported physical type");
     const bool nested = a.leaf.n_nested > 1;
     if (a.leaf.n_nested > SB_MAX_NESTED) return fail(ctx, SB_NYI, "nesting deeper than SB_MAX_NESTED");
     EncCol &ec = h_cols[c];
@@ -407,7 +409,7 @@ int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_col
     ec.type = a.leaf.type;
     ec.nullable = a.leaf.nullable != 0;
     ec.W = type_width(a.leaf.type);
-    ec.tclass = (a.leaf.type == SB_F32 || a.leaf.type == SB_F64) ? TC_FLOAT : (a.leaf.type >= SB_I8 && a.leaf.type <= SB_I64) ? TC_SINT : TC_UINT;
+    ec.tclass = (a.leaf.type == SB_F32 || a.leaf.type == SB_F64) ? TC_FLOAT : ((a.leaf.type >= SB_I8 && a.leaf.type <= SB_I64) || a.leaf.type >= SB_I128) ? TC_SINT : TC_UINT;
     ec.length = a.length;
     ec.values_bytes = a.values_bytes;
     const bool binary = a.leaf.type == SB_BINARY || a.leaf.type == SB_LARGE_BINARY;
@@ -421,7 +423,7 @@ int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_col
       free_inputs();
       return rc;
     }
-    if (fixed_type(a.leaf.type) && (uintptr_t(ec.values) % uintptr_t(ec.W)) != 0) {
+    if (fixed_type(a.leaf.type) && (uintptr_t(ec.values) % uintptr_t(std::min(ec.W, 16))) != 0) {
       free_inputs();
       return fail(ctx, SB_INVALID_ARG, "values must be aligned to the element width");
     }

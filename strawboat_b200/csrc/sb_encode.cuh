@@ -174,6 +174,7 @@ struct EffFixed {
     return uint32_t(k >> 32) ^ uint32_t(k);
   }
   __device__ __forceinline__ bool equal(uint32_t i, uint32_t j) const { return key(i) == key(j); }
+  __device__ __forceinline__ void put(uint8_t *out, uint32_t i, int W) const { st_le(out, key(i), W); }
 };
 
 // ------------------------------------------------------------------------------------
@@ -411,7 +412,7 @@ __device__ uint32_t enc_rle(Dctx &cx, const Acc &acc, uint32_t n, int W, uint8_t
       uint32_t s = starts[r], e = r + 1 < nruns ? starts[r + 1] : n;
       uint8_t *o = out + uint64_t(r) * (4 + W);
       st_le(o, e - s, 4);
-      st_le(o + 4, acc.key(s), W);
+      acc.put(o + 4, s, W);
     }
     __syncthreads();
   }
@@ -995,6 +996,381 @@ __device__ uint32_t enc_fixed(Dctx &cx, Vals v, int tclass, Bits valid, uint32_t
 }
 
 // ------------------------------------------------------------------------------------
+// i128 / i256 leaves (Decimal128 / Decimal256 storage; compress_integer over `i128` / `i256`,
+// src/write/primitive.rs:71-78, src/compression/integer/traits.rs:28-39).  Same statistics and chooser as
+// enc_fixed; Bitpacking / DeltaBitpacking never apply (size_of::<T>() != 4, bp.rs:93-97), Patas is float only.
+// Values are moved as 16-byte vectors and compared word by word; ordering (for `max.as_i64() >= 256`,
+// freq.rs:146) is signed two's complement.
+// ------------------------------------------------------------------------------------
+struct EffWide {
+  const uint8_t *p;    // 16-byte aligned values
+  int W;               // 16 or 32
+  const uint32_t *src; // null replacement rows (nullptr: identity); kNone = leading null
+  uint32_t lead;       // row whose value leading nulls take, kNone = T::default() (zero)
+  __device__ __forceinline__ uint32_t row(uint32_t i) const {
+    uint32_t r = src ? src[i] : i;
+    return r == kNone ? lead : r;
+  }
+  __device__ __forceinline__ uint4 vec(uint32_t r, int k) const {
+    return r == kNone ? make_uint4(0, 0, 0, 0) : reinterpret_cast<const uint4 *>(p + uint64_t(r) * W)[k];
+  }
+  __device__ __forceinline__ uint32_t hash(uint32_t i) const {
+    const uint32_t r = row(i);
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (int k = 0; k < W / 16; ++k) {
+      const uint4 v = vec(r, k);
+      h = (h ^ (uint64_t(v.x) | (uint64_t(v.y) << 32))) * 0xBF58476D1CE4E5B9ull;
+      h = (h ^ (h >> 29) ^ (uint64_t(v.z) | (uint64_t(v.w) << 32))) * 0x94D049BB133111EBull;
+    }
+    return uint32_t(h >> 32) ^ uint32_t(h);
+  }
+  __device__ __forceinline__ bool equal(uint32_t i, uint32_t j) const {
+    const uint32_t a = row(i), b = row(j);
+    if (a == b) return true;
+    for (int k = 0; k < W / 16; ++k) {
+      const uint4 x = vec(a, k), y = vec(b, k);
+      if (x.x != y.x || x.y != y.y || x.z != y.z || x.w != y.w) return false;
+    }
+    return true;
+  }
+  __device__ __forceinline__ void put(uint8_t *out, uint32_t i, int) const { // out: any alignment
+    const uint32_t r = row(i);
+    for (int k = 0; k < W / 16; ++k) {
+      const uint4 v = vec(r, k);
+      st_le(out + 16 * k, v.x, 4), st_le(out + 16 * k + 4, v.y, 4), st_le(out + 16 * k + 8, v.z, 4), st_le(out + 16 * k + 12, v.w, 4);
+    }
+  }
+  // signed compare of the raw values at rows a, b
+  __device__ __forceinline__ bool less(uint32_t a, uint32_t b) const {
+    for (int k = W / 16 - 1; k >= 0; --k) {
+      const uint4 x = vec(a, k), y = vec(b, k);
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+      for (int w = 3; w >= 0; --w) {
+        if (xs[w] == ys[w]) continue;
+        if (k == W / 16 - 1 && w == 3) return int32_t(xs[w]) < int32_t(ys[w]);
+        return xs[w] < ys[w];
+      }
+    }
+    return false;
+  }
+};
+
+// ids in first-occurrence order from a distinct table (shared by the wide Dict path; enc_fixed / enc_binary carry
+// the same steps inline): on return slot_of[row] = id, dt.cnt[slot] = id of that slot.  idx is scratch (n entries).
+__device__ void dict_assign_ids(Dctx &cx, HashTab &dt, uint32_t *slot_of, uint32_t *idx, uint32_t n) {
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < n; i += SB_NT) idx[i] = 0;
+  __syncthreads();
+  for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
+    if (dt.rep[h]) idx[dt.first[h]] = 1;
+  __syncthreads();
+  constexpr uint32_t EPT = 8, CH = SB_NT * EPT;
+  uint32_t run = 0;
+  for (uint32_t c0 = 0; c0 < n; c0 += CH) {
+    const uint32_t e0 = c0 + tid * EPT;
+    uint32_t f[EPT], c = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < EPT; ++j) {
+      f[j] = e0 + j < n ? idx[e0 + j] : 0;
+      c += f[j];
+    }
+    uint32_t total;
+    uint32_t pre = run + block_excl_scan(c, cx.ws, &total);
+#pragma unroll
+    for (uint32_t j = 0; j < EPT; ++j)
+      if (e0 + j < n) {
+        idx[e0 + j] = pre;
+        pre += f[j];
+      }
+    run += total;
+  }
+  __syncthreads();
+  for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
+    if (dt.rep[h]) dt.cnt[h] = idx[dt.first[h]];
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += SB_NT) slot_of[i] = dt.cnt[slot_of[i]];
+  __syncthreads();
+}
+
+__device__ uint32_t first_valid_row(Dctx &cx, const Bits &valid, uint32_t n) {
+  if (threadIdx.x == 0) cx.bcast[2] = int(kNone);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += SB_NT)
+    if (valid.get(i)) {
+      atomicMin(reinterpret_cast<uint32_t *>(cx.bcast + 2), i);
+      break;
+    }
+  __syncthreads();
+  const uint32_t fv = uint32_t(cx.bcast[2]);
+  __syncthreads();
+  return fv;
+}
+
+template <int LEVEL>
+__device__ uint32_t enc_wide(Dctx &cx, const uint8_t *vals, int W, Bits valid, uint32_t n, EOpts o, uint8_t *out) {
+  const uint32_t tid = threadIdx.x;
+  Arena mark = cx.ar;
+  uint8_t *body = out + 9;
+  // ---- gen_stats: null count, max (signed, over all slots), distinct table over all slots
+  EffWide raw{vals, W, nullptr, kNone};
+  uint32_t nulls = 0, best = kNone;
+  for (uint32_t i = tid; i < n; i += SB_NT) {
+    nulls += !valid.get(i);
+    if (best == kNone || raw.less(best, i)) best = i;
+  }
+  const uint32_t null_count = uint32_t(block_sum_u64e(cx, nulls));
+  bool max_ge_256 = false;
+  {
+    uint32_t *cand = static_cast<uint32_t *>(cx.ar.alloc(SB_NT * 4));
+    if (!cand) {
+      cx.flag(SB_NYI);
+      return kEncFail;
+    }
+    cand[tid] = best;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t b = kNone;
+      for (uint32_t t = 0; t < SB_NT; ++t)
+        if (cand[t] != kNone && (b == kNone || raw.less(b, cand[t]))) b = cand[t];
+      int64_t lo64 = 0;
+      if (b != kNone) {
+        const uint4 v = raw.vec(b, 0);
+        lo64 = int64_t(uint64_t(v.x) | (uint64_t(v.y) << 32)); // as_i64: the low 64 bits (traits.rs:28-39)
+      }
+      cx.bcast[3] = lo64 >= 256;
+    }
+    __syncthreads();
+    max_ge_256 = cx.bcast[3] != 0;
+    __syncthreads();
+    cx.ar = mark;
+  }
+  HashTab tab{};
+  const uint32_t limit = n / 3 + 1;
+  uint32_t unique = n ? hash_distinct(cx, raw, n, limit, &tab, nullptr) : 0;
+  if (*cx.err) return kEncFail;
+  uint32_t max_count = 0, top_first = 0;
+  if (unique != kNone && n) hash_top(cx, tab, &max_count, &top_first);
+  cx.ar = mark;
+  const bool exact_small = unique != kNone, one = n && exact_small && unique <= 1;
+  const bool has_nulls = valid.p && null_count;
+
+  // null replacement rows (RLE / Dict), first valid row
+  uint32_t *src = nullptr;
+  auto need_src = [&]() -> bool {
+    if (!has_nulls || src) return true;
+    src = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
+    if (!src) {
+      cx.flag(SB_NYI);
+      return false;
+    }
+    fill_forward(cx, valid, n, false, src);
+    return true;
+  };
+
+  // ---- choose_compressor (integer/mod.rs:231-308): OneValue, Freq, Dict, RLE (Bitpacking / Delta: ratio 0 for this width)
+  int codec = o.def_codec;
+  auto rle_sample_ratio = [&]() -> double { // compress_sample_ratio on 10 x 64 rows (integer/mod.rs:310-347)
+    Arena m2 = cx.ar;
+    const uint32_t m = sample_whole(n) ? n : 640;
+    uint8_t *sv = static_cast<uint8_t *>(cx.ar.alloc(uint64_t(m) * W + 16));
+    uint8_t *sb = static_cast<uint8_t *>(cx.ar.alloc((m + 7) / 8 + 16));
+    uint32_t *ssrc = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(m) * 4 + 16));
+    if (!sv || !sb || !ssrc) {
+      cx.flag(SB_NYI);
+      return 0.0;
+    }
+    for (uint32_t i = tid; i < (m + 7) / 8; i += SB_NT) {
+      uint32_t byte = 0;
+      for (uint32_t b = 0; b < 8 && 8 * i + b < m; ++b) {
+        const uint32_t r = sample_whole(n) ? 8 * i + b : sample_row(n, o, SB_C_RLE, 8 * i + b);
+        byte |= uint32_t(valid.get(r)) << b;
+      }
+      sb[i] = uint8_t(byte);
+    }
+    for (uint32_t k = tid; k < m; k += SB_NT) {
+      const uint32_t r = sample_whole(n) ? k : sample_row(n, o, SB_C_RLE, k);
+      for (int q = 0; q < W / 16; ++q) reinterpret_cast<uint4 *>(sv + uint64_t(k) * W)[q] = raw.vec(r, q);
+    }
+    __syncthreads();
+    EffWide acc{sv, W, nullptr, kNone};
+    if (has_nulls) {
+      const Bits sbits{sb, 0};
+      fill_forward(cx, sbits, m, false, ssrc);
+      acc.src = ssrc;
+      acc.lead = first_valid_row(cx, sbits, m);
+    }
+    const uint32_t size = enc_rle(cx, acc, m, W, nullptr, true);
+    cx.ar = m2;
+    return size == kEncFail || size == 0 ? 0.0 : double(uint64_t(m) * W) / double(size);
+  };
+  if (o.force >= SB_C_RLE && !e_forbidden(o, o.force) &&
+      (o.force == SB_C_FREQ || o.force == SB_C_DICT || o.force == SB_C_RLE || (o.force == SB_C_ONEVALUE && (n == 0 || one)))) {
+    codec = o.force;
+  } else if (o.ratio >= 0 && n) {
+    double max_ratio = o.ratio;
+    const int order[4] = {SB_C_ONEVALUE, SB_C_FREQ, SB_C_DICT, SB_C_RLE};
+    for (int k = 0; k < 4; ++k) {
+      const int c = order[k];
+      if (e_forbidden(o, c)) continue;
+      double r = 0.0;
+      switch (c) {
+      case SB_C_ONEVALUE: r = one ? double(n) : 0.0; break;
+      case SB_C_FREQ:
+        if (exact_small && unique <= 1) r = 0.0;
+        else if (double(null_count) / double(n) >= 0.9) r = double(n - 1);
+        else if (exact_small && double(max_count) / double(n) >= 0.9 && max_ge_256) r = double(n - 1);
+        break;
+      case SB_C_DICT:
+        if (exact_small && uint64_t(unique) * 3 < n) {
+          const uint64_t after = uint64_t(unique) * W + uint64_t(n) * (bits_needed(unique) / 8) + uint64_t(n) * 2 / 128;
+          r = double(uint64_t(n) * W) / double(after);
+        }
+        break;
+      case SB_C_RLE: r = rle_sample_ratio(); break;
+      }
+      if (r > max_ratio) {
+        max_ratio = r;
+        codec = c;
+        if (r == double(n)) break;
+      }
+    }
+  }
+  if (*cx.err) return kEncFail;
+
+  uint32_t payload = 0;
+  switch (codec) {
+  case SB_C_NONE:
+  case SB_C_LZ4:
+  case SB_C_ZSTD:
+  case SB_C_SNAPPY: payload = enc_basic(cx, codec, vals, n * uint32_t(W), body); break;
+  case SB_C_ONEVALUE: { // first valid value, else default (one_value.rs:61-75)
+    const uint32_t fv = n ? first_valid_row(cx, valid, n) : kNone;
+    if (tid == 0) {
+      if (fv != kNone) EffWide{vals, W, nullptr, kNone}.put(body, fv, W);
+      else
+        for (int b = 0; b < W; ++b) body[b] = 0;
+    }
+    payload = W;
+    break;
+  }
+  case SB_C_RLE: {
+    if (!need_src()) return kEncFail;
+    EffWide acc{vals, W, src, has_nulls ? first_valid_row(cx, valid, n) : kNone};
+    payload = enc_rle(cx, acc, n, W, body, false);
+    break;
+  }
+  case SB_C_DICT: {
+    if constexpr (LEVEL >= 2) {
+      cx.flag(SB_OUT_OF_SPEC);
+      return kEncFail;
+    } else {
+      if (!need_src()) return kEncFail;
+      EffWide acc{vals, W, src, kNone}; // leading nulls intern T::default()
+      uint32_t *slot_of = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
+      uint32_t *idx = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
+      if (!slot_of || !idx) {
+        cx.flag(SB_NYI);
+        return kEncFail;
+      }
+      HashTab dt{};
+      const uint32_t k = hash_distinct(cx, acc, n, n + 1, &dt, slot_of);
+      if (*cx.err || k == kNone) return kEncFail;
+      dict_assign_ids(cx, dt, slot_of, idx, n);
+      EOpts sub = o;
+      sub.forbidden |= 1u << SB_C_DICT;
+      const uint32_t used = enc_fixed<LEVEL + 1>(cx, Vals{reinterpret_cast<const uint8_t *>(slot_of), 4}, TC_UINT, Bits{nullptr, 0}, n, sub, body);
+      if (used == kEncFail) return kEncFail;
+      if (tid == 0) st_le(body + used, k, 4);
+      uint8_t *tabo = body + used + 4;
+      for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
+        if (dt.rep[h]) acc.put(tabo + uint64_t(dt.cnt[h]) * W, dt.first[h], W);
+      __syncthreads();
+      payload = used + 4 + k * uint32_t(W);
+    }
+    break;
+  }
+  case SB_C_FREQ: {
+    if constexpr (LEVEL >= 2) {
+      cx.flag(SB_OUT_OF_SPEC);
+      return kEncFail;
+    } else {
+      const bool top_is_null = n && double(null_count) / double(n) >= 0.9;
+      uint32_t top_row = kNone; // kNone = T::default()
+      if (!top_is_null && n) {
+        if (unique == kNone) { // forced Freq on high-cardinality data: needs the full table
+          HashTab ft{};
+          const uint32_t k = hash_distinct(cx, raw, n, n + 1, &ft, nullptr);
+          if (*cx.err || k == kNone) return kEncFail;
+          hash_top(cx, ft, &max_count, &top_first);
+        }
+        top_row = top_first;
+      }
+      uint32_t *rows = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
+      uint8_t *exc = static_cast<uint8_t *>(cx.ar.alloc(uint64_t(n) * W + 16));
+      if (!rows || !exc) {
+        cx.flag(SB_NYI);
+        return kEncFail;
+      }
+      const EffWide cmp{vals, W, nullptr, kNone};
+      uint32_t n_exc = 0;
+      constexpr uint32_t EPT = 4, CH = SB_NT * EPT;
+      for (uint32_t c0 = 0; c0 < n; c0 += CH) {
+        const uint32_t e0 = c0 + tid * EPT;
+        uint32_t flags = 0, c = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < EPT; ++j) {
+          const uint32_t i = e0 + j;
+          bool differs = false;
+          if (i < n && valid.get(i)) {
+            if (top_is_null) differs = true;
+            else
+              for (int q = 0; q < W / 16; ++q) {
+                const uint4 x = cmp.vec(i, q), y = cmp.vec(top_row, q);
+                differs |= x.x != y.x || x.y != y.y || x.z != y.z || x.w != y.w;
+              }
+          }
+          if (differs) {
+            flags |= 1u << j;
+            ++c;
+          }
+        }
+        uint32_t total;
+        uint32_t pre = n_exc + block_excl_scan(c, cx.ws, &total);
+#pragma unroll
+        for (uint32_t j = 0; j < EPT; ++j)
+          if ((flags >> j) & 1u) {
+            rows[pre] = e0 + j;
+            for (int q = 0; q < W / 16; ++q) reinterpret_cast<uint4 *>(exc + uint64_t(pre) * W)[q] = cmp.vec(e0 + j, q);
+            ++pre;
+          }
+        n_exc += total;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        if (top_row != kNone) cmp.put(body, top_row, W);
+        else
+          for (int b = 0; b < W; ++b) body[b] = 0;
+      }
+      const uint32_t bm = enc_roaring(cx, rows, n_exc, n, body + W + 4);
+      if (tid == 0) st_le(body + W, bm, 4);
+      EOpts sub = o;
+      sub.forbidden |= 1u << SB_C_FREQ;
+      const uint32_t used = enc_wide<LEVEL + 1>(cx, exc, W, Bits{nullptr, 0}, n_exc, sub, body + W + 4 + bm);
+      if (used == kEncFail) return kEncFail;
+      payload = uint32_t(W) + 4 + bm + used;
+    }
+    break;
+  }
+  default: cx.flag(SB_OUT_OF_SPEC); return kEncFail;
+  }
+  if (payload == kEncFail || *cx.err) return kEncFail;
+  put_hdr9(out, codec, payload, n * uint32_t(W));
+  __syncthreads();
+  cx.ar = mark;
+  return 9 + payload;
+}
+
+// ------------------------------------------------------------------------------------
 // write_validity (write/serialize.rs:200-215): [u32 L][ULEB((ceil8(n) << 1) | 1)][bitmap],
 // written for every nullable field, all ones when the array carries no validity.
 // ------------------------------------------------------------------------------------
@@ -1034,6 +1410,7 @@ struct EffBool {
     return s == kNone ? lead : uint32_t(v.get(s));
   }
   __device__ __forceinline__ bool equal(uint32_t i, uint32_t j) const { return key(i) == key(j); }
+  __device__ __forceinline__ void put(uint8_t *out, uint32_t i, int W) const { st_le(out, key(i), W); }
 };
 __device__ uint32_t bool_rle(Dctx &cx, const Bits &vals, const Bits &valid, uint32_t n, bool has_nulls, uint8_t *out, bool count_only) {
   Arena mark = cx.ar;

@@ -110,11 +110,13 @@ inline int type_width(int t) {
   case SB_I64:
   case SB_U64:
   case SB_F64: return 8;
+  case SB_I128: return 16;
+  case SB_I256: return 32;
   case SB_BINARY: return 4;
   case SB_LARGE_BINARY: return 8;
   }
   return 0;
 }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-inline bool fixed_type(int t) { return t >= SB_I8 && t <= SB_F64; }
+inline bool fixed_type(int t) { return (t >= SB_I8 && t <= SB_F64) || t == SB_I128 || t == SB_I256; }
 

@@ -23,7 +23,7 @@
 
 namespace sb {
 
-__device__ __forceinline__ bool is_fixed_type(int t) { return t >= SB_I8 && t <= SB_F64; }
+__device__ __forceinline__ bool is_fixed_type(int t) { return (t >= SB_I8 && t <= SB_F64) || t == SB_I128 || t == SB_I256; }
 
 constexpr uint32_t kSmemMax = 74 * 1024;     // dynamic shared memory per CTA: 3 CTAs / SM
 constexpr uint32_t kSmemMin = 40 * 1024;
@@ -98,29 +98,43 @@ __device__ __forceinline__ bool lz4_stored_block(const uint8_t *s, uint32_t clen
   return __all_sync(0xffffffffu, ok);
 }
 
+__device__ __forceinline__ uint32_t ldg_u32u(const uint8_t *p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); }
+
 __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, uint32_t n_pages,
-                                   Lz4Job *jobs, uint32_t *n_jobs, uint8_t *side_flags) {
+                                   Lz4Job *jobs, uint32_t *n_jobs, uint8_t *side_flags, const PageAux *__restrict__ aux) {
   const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_pages) return;
   const PageDesc pg = pages[i];
   const ColDesc col = cols[pg.col];
-  if (!is_fixed_type(col.type) || col.n_nested > 1) return;
+  if (!is_fixed_type(col.type)) return;
+  const bool nested = col.n_nested > 1;
   uint32_t vb, clen;
-  if (plain_page(pg.src, pg.len, col.nullable != 0, uint64_t(pg.num_values) * uint32_t(col.W))) {
+  uint64_t n_vals = pg.num_values;
+  const uint8_t *body = pg.src;
+  uint32_t body_len = pg.len;
+  if (nested) {
+    // [u32 rows][u32 rep_len][u32 def_len][rep][def][VALUE_BLOCK over the leaf slots]: the plan pass counted the slots
+    if (pg.len < 12 || pg.aux == 0xffffffffu) return;
+    const uint64_t lv = 12ull + ldg_u32u(pg.src + 4) + ldg_u32u(pg.src + 8);
+    if (lv > pg.len) return;
+    body += lv;
+    body_len -= uint32_t(lv);
+    n_vals = aux[pg.aux].cnt[col.n_nested - 1];
+  } else if (plain_page(pg.src, pg.len, col.nullable != 0, uint64_t(pg.num_values) * uint32_t(col.W))) {
     if (lane == 0) side_flags[i] = 3;
     return;
   }
-  if (!lz4_side_page(pg.src, pg.len, col.nullable != 0, &vb, &clen)) return;
-  const uint64_t dlen64 = uint64_t(pg.num_values) * uint32_t(col.W);
+  if (!lz4_side_page(body, body_len, !nested && col.nullable != 0, &vb, &clen)) return;
+  const uint64_t dlen64 = n_vals * uint32_t(col.W);
   if (dlen64 > SB_LZ4_MAXPOS / 2 || clen > SB_LZ4_MAXPOS / 2) return; // positions are 30-bit in sb_lz4_kernel
   const uint32_t dlen = uint32_t(dlen64);
-  if (lz4_stored_block(pg.src + vb + 9, clen, dlen)) {
+  if (lz4_stored_block(body + vb + 9, clen, dlen)) {
     if (lane == 0) side_flags[i] = 2;
     return;
   }
   if (lane != 0) return;
   Lz4Job j;
-  j.src = pg.src + vb + 9;
+  j.src = body + vb + 9;
   j.dst = col.values + pg.out_elem * uint64_t(col.W);
   j.clen = clen;
   j.dlen = dlen;
@@ -243,14 +257,14 @@ __global__ void __launch_bounds__(SB_NT, 4)
     const uint32_t side = (pass == 1 && side_flags != nullptr) ? side_flags[wi.page] : 0u;
     const bool lz4_side = side == 1; // value block decoded by sb_lz4_kernel
     const bool stored = side == 2;   // LZ4 block that is one literal run: plain copy here
-    if (lz4_side && !col.nullable) { // value block handled by sb_lz4_kernel, nothing else in the page
+    if (lz4_side && !col.nullable && col.n_nested <= 1) { // value block handled by sb_lz4_kernel, nothing else in the page
       if (tid == 0 && (wi.tile == 0 || wi.tile == 0xffffffffu)) atomicAdd(codec_hist + SB_C_LZ4, 1u);
       __syncthreads();
       if (tid == 0) s_item = next_it;
       __syncthreads();
       continue;
     }
-    const bool plain = side == 3;    // codec None, header validated by sb_classify_kernel
+    const bool plain = side == 3;    // flat page, codec None, header validated by sb_classify_kernel
     // plain pages stage only what precedes the value bytes (validity section + hdr9; nothing when not nullable)
     const uint32_t stage_len = plain ? pg.len - pg.num_values * uint32_t(col.W) : pg.len;
     const bool staged = stage_len + 32 <= stage_cap && !(plain && !col.nullable);
@@ -319,6 +333,8 @@ __global__ void __launch_bounds__(SB_NT, 4)
         case 1: dec_onevalue<1>(cx, p + 9, avail - 9, lo, hi, dst); break;
         case 2: dec_onevalue<2>(cx, p + 9, avail - 9, lo, hi, dst); break;
         case 4: dec_onevalue<4>(cx, p + 9, avail - 9, lo, hi, dst); break;
+        case 16: dec_onevalue<16>(cx, p + 9, avail - 9, lo, hi, dst); break;
+        case 32: dec_onevalue<32>(cx, p + 9, avail - 9, lo, hi, dst); break;
         default: dec_onevalue<8>(cx, p + 9, avail - 9, lo, hi, dst); break;
         }
       } else if (wi.tile == 0) {
@@ -658,7 +674,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   auto col_nested = [](const sb_column_in &ci) { return ci.leaf.n_nested > 1; };
   for (uint64_t c = 0; c < n_cols; ++c) {
     const sb_column_in &ci = cols[c];
-    if (ci.leaf.type < SB_NULL || ci.leaf.type > SB_LARGE_BINARY) return fail(ctx, SB_NYI, "unsupported physical type");
+    if (ci.leaf.type < SB_NULL || ci.leaf.type > SB_I256) return fail(ctx, SB_NYI, "unsupported physical type");
     if (ci.leaf.n_nested > SB_MAX_NESTED) return fail(ctx, SB_NYI, "nesting deeper than SB_MAX_NESTED");
     if (col_nested(ci)) {
       if (ci.leaf.nested_kind[ci.leaf.n_nested - 1] != SB_N_PRIMITIVE) return fail(ctx, SB_INVALID_ARG, "the last nested entry must be the primitive leaf");
@@ -764,7 +780,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     owners[c] = ow;
     const int W = type_width(ci.leaf.type);
     const bool nested = col_nested(ci), binary = col_binary(ci);
-    any_fixed |= fixed_type(ci.leaf.type) && !nested;
+    any_fixed |= fixed_type(ci.leaf.type);
     uint64_t rows = 0, total_len = 0;
     for (uint64_t p = 0; p < ci.n_pages; ++p) {
       rows += ci.metas[p].num_values;
@@ -981,7 +997,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_fork, st));
       SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
       sb_classify_kernel<<<uint32_t((n_pages_total + 7) / 8), 256, 0, ctx->aux>>>(d_pages, d_cols, uint32_t(n_pages_total), d_jobs,
-                                                                                    d_counters + 2, d_flags);
+                                                                                    d_counters + 2, d_flags, d_aux);
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_cls, ctx->aux));
       if (ctx->lz4_occ == 0) {
         int q = 1;
