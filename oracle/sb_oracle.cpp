@@ -241,6 +241,121 @@ int lz4_block_decode(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_
 // ---------------------------------------------------------------------------------
 // CommonCompression (src/compression/basic.rs:62-152)
 // ---------------------------------------------------------------------------------
+// ---- Snappy raw format (snap = "1.1.0" raw::{Encoder,Decoder}; format_description.txt of google/snappy):
+// [varint uncompressed length] then elements: tag & 3 == 0 literal (len-1 in the upper 6 bits, 60..63 => 1..4
+// little-endian length bytes follow), 1 = copy with 11-bit offset and length 4..11, 2 = copy with 16-bit offset
+// and length 1..64, 3 = copy with 32-bit offset.  The crate source is absent (FORMAT_ASSUMPTIONS #5): pinned
+// against pyarrow's snappy codec (Google's C++ library) in tests/test_oracle_thirdparty.py.
+int snappy_decompress(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len) {
+  size_t ip = 0;
+  uint64_t n = 0;
+  for (unsigned shift = 0;; shift += 7) {
+    if (ip >= in_len || shift > 28) return fail(SBO_EXTERNAL, "decompress snappy faild: header");
+    uint8_t b = in[ip++];
+    n |= uint64_t(b & 0x7f) << shift;
+    if (!(b & 0x80)) break;
+  }
+  if (n != out_len) return fail(SBO_EXTERNAL, "decompress snappy faild: length mismatch"); // snap: BufferTooSmall when larger
+  size_t op = 0;
+  while (ip < in_len) {
+    const uint8_t tag = in[ip++];
+    size_t len, offset;
+    switch (tag & 3) {
+    case 0: {
+      len = size_t(tag >> 2) + 1;
+      if (len > 60) {
+        const size_t nb = len - 60;
+        if (in_len - ip < nb) return fail(SBO_EXTERNAL, "decompress snappy faild: literal length");
+        len = 0;
+        for (size_t k = 0; k < nb; ++k) len |= size_t(in[ip + k]) << (8 * k);
+        len += 1;
+        ip += nb;
+      }
+      if (len > in_len - ip || len > out_len - op) return fail(SBO_EXTERNAL, "decompress snappy faild: literal");
+      std::memcpy(out + op, in + ip, len);
+      ip += len;
+      op += len;
+      continue;
+    }
+    case 1:
+      if (ip >= in_len) return fail(SBO_EXTERNAL, "decompress snappy faild: copy1");
+      len = 4 + ((tag >> 2) & 7);
+      offset = (size_t(tag >> 5) << 8) | in[ip++];
+      break;
+    case 2:
+      if (in_len - ip < 2) return fail(SBO_EXTERNAL, "decompress snappy faild: copy2");
+      len = size_t(tag >> 2) + 1;
+      offset = size_t(in[ip]) | (size_t(in[ip + 1]) << 8);
+      ip += 2;
+      break;
+    default:
+      if (in_len - ip < 4) return fail(SBO_EXTERNAL, "decompress snappy faild: copy4");
+      len = size_t(tag >> 2) + 1;
+      offset = size_t(load_le<uint32_t>(in + ip));
+      ip += 4;
+      break;
+    }
+    if (offset == 0 || offset > op || len > out_len - op) return fail(SBO_EXTERNAL, "decompress snappy faild: copy");
+    for (size_t k = 0; k < len; ++k) out[op + k] = out[op - offset + k]; // byte order matters: copies may overlap
+    op += len;
+  }
+  if (op != out_len) return fail(SBO_EXTERNAL, "decompress snappy faild: short stream");
+  return SBO_OK;
+}
+// greedy 4-byte-hash matcher; any valid stream decodes with the reference's snap::raw::Decoder
+void snappy_compress(const uint8_t *in, size_t n, Bytes &out) {
+  for (uint64_t v = n;;) {
+    uint8_t b = v & 0x7f;
+    v >>= 7;
+    out.push_back(b | (v ? 0x80 : 0));
+    if (!v) break;
+  }
+  auto emit_literal = [&](size_t from, size_t len) {
+    if (!len) return;
+    const size_t l1 = len - 1;
+    if (l1 < 60) out.push_back(uint8_t(l1 << 2));
+    else {
+      int nb = l1 < (1u << 8) ? 1 : l1 < (1u << 16) ? 2 : l1 < (1u << 24) ? 3 : 4;
+      out.push_back(uint8_t((59 + nb) << 2));
+      for (int k = 0; k < nb; ++k) out.push_back(uint8_t(l1 >> (8 * k)));
+    }
+    put_bytes(out, in + from, len);
+  };
+  auto emit_copy = [&](size_t offset, size_t len) {
+    while (len) {
+      size_t l = len > 64 ? (len - 64 < 4 ? 60 : 64) : len; // never leave a tail shorter than 4 (it fits copy2 anyway)
+      if (l >= 4 && l <= 11 && offset < 2048) {
+        out.push_back(uint8_t(1 | ((l - 4) << 2) | ((offset >> 8) << 5)));
+        out.push_back(uint8_t(offset));
+      } else {
+        out.push_back(uint8_t(2 | ((l - 1) << 2)));
+        out.push_back(uint8_t(offset));
+        out.push_back(uint8_t(offset >> 8));
+      }
+      len -= l;
+    }
+  };
+  std::vector<int64_t> table(1 << 14, -1);
+  size_t ip = 0, anchor = 0;
+  while (n >= 8 && ip + 4 <= n) {
+    const uint32_t seq = load_le<uint32_t>(in + ip);
+    const uint32_t h = (seq * 0x1e35a7bdu) >> 18;
+    const int64_t cand = table[h];
+    table[h] = int64_t(ip);
+    if (cand >= 0 && ip - size_t(cand) <= 65535 && load_le<uint32_t>(in + cand) == seq) {
+      size_t ml = 4;
+      while (ip + ml < n && in[cand + ml] == in[ip + ml]) ++ml;
+      emit_literal(anchor, ip - anchor);
+      emit_copy(ip - size_t(cand), ml);
+      ip += ml;
+      anchor = ip;
+    } else {
+      ++ip;
+    }
+  }
+  emit_literal(anchor, n - anchor);
+}
+
 int common_decompress(int codec, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len) {
   switch (codec) {
   case SBO_C_NONE: // basic.rs:67-70 copy_from_slice panics on length mismatch
@@ -260,7 +375,7 @@ int common_decompress(int codec, const uint8_t *in, size_t in_len, uint8_t *out,
     return SBO_OK;
   }
   default:
-    return fail(SBO_NYI, "snappy not available in the oracle");
+    return snappy_decompress(in, in_len, out, out_len); // basic.rs:98-105
   }
 }
 
@@ -291,8 +406,13 @@ int common_compress(int codec, const uint8_t *in, size_t in_len, Bytes &out, siz
     written = r;
     return SBO_OK;
   }
-  default:
-    return fail(SBO_NYI, "snappy not available in the oracle");
+  case SBO_C_SNAPPY: { // basic.rs:138-152
+    const size_t start = out.size();
+    snappy_compress(in, in_len, out);
+    written = out.size() - start;
+    return SBO_OK;
+  }
+  default: return fail(SBO_OUT_OF_SPEC, "not a common codec");
   }
 }
 
@@ -1987,6 +2107,17 @@ int sbo_lz4_compress_lib(const uint8_t *in, size_t in_len, sbo_buf *out) {
   if (rc) return rc;
   export_buf(b, out);
   return SBO_OK;
+}
+int sbo_common_compress(int32_t codec, const uint8_t *in, size_t in_len, sbo_buf *out) {
+  Bytes b;
+  size_t w = 0;
+  int rc = common_compress(codec, in, in_len, b, w);
+  if (rc) return rc;
+  export_buf(b, out);
+  return SBO_OK;
+}
+int sbo_common_decompress(int32_t codec, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len) {
+  return common_decompress(codec, in, in_len, out, out_len);
 }
 uint16_t sbo_patas_pack(uint8_t r, uint8_t s, uint8_t t) { return patas_pack(r, s, t); }
 void sbo_patas_unpack(uint16_t p, uint8_t *o) { patas_unpack(p, o[0], o[1], o[2]); }

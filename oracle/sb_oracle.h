@@ -164,6 +164,9 @@ size_t sbo_bp4x_compress_sorted(uint32_t initial, const uint32_t *in128, uint8_t
 size_t sbo_bp4x_decompress_sorted(uint32_t initial, const uint8_t *in, uint32_t *out128, uint32_t num_bits);
 int sbo_roaring_serialize(const uint32_t *sorted_vals, size_t n, sbo_buf *out);
 int sbo_roaring_deserialize(const uint8_t *in, size_t len, sbo_buf *out_u32);
+/* CommonCompression::{compress,decompress} (basic.rs:62-152) for one buffer */
+int sbo_common_compress(int32_t codec, const uint8_t *in, size_t in_len, sbo_buf *out);
+int sbo_common_decompress(int32_t codec, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
 int sbo_lz4_decompress(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len); /* own block decoder */
 int sbo_lz4_decompress_lib(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len); /* liblz4 */
 int sbo_lz4_compress_lib(const uint8_t *in, size_t in_len, sbo_buf *out);

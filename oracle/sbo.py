@@ -398,6 +398,20 @@ def lz4_compress(data):
     return _take(buf)
 
 
+def common_compress(codec, data):
+    b = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data if len(data) else b"\0")
+    buf = Buf()
+    _check(lib().sbo_common_compress(codec, b, C.c_size_t(len(data)), C.byref(buf)))
+    return _take(buf)
+
+
+def common_decompress(codec, data, out_len):
+    b = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data if len(data) else b"\0")
+    out = np.zeros(max(1, out_len), dtype=np.uint8)
+    _check(lib().sbo_common_decompress(codec, b, C.c_size_t(len(data)), out.ctypes.data_as(C.c_void_p), C.c_size_t(out_len)))
+    return out[:out_len].tobytes()
+
+
 def patas_pack(r, s, t):
     return lib().sbo_patas_pack(C.c_uint8(r), C.c_uint8(s), C.c_uint8(t))
 

@@ -110,6 +110,86 @@ __device__ __noinline__ bool dec_lz4_block(Dctx &cx, const uint8_t *src, uint32_
     return true;
 }
 
+// ------------------------------------------------------------------------------------
+// Snappy raw block (basic.rs:98-105 -> snap::raw::Decoder::decompress; format: google/snappy
+// format_description.txt).  [varint n] then elements: literal (tag & 3 == 0), copy with 11-bit /
+// 16-bit / 32-bit offset.  One warp walks the elements (the tag chain is serial) and moves the
+// bytes of each element lane-parallel.  Returns 0 or SB_EXTERNAL, uniform over the warp.
+// ------------------------------------------------------------------------------------
+__device__ int snappy_decode_warp(const uint8_t *src, uint32_t clen, uint8_t *dst, uint32_t dlen) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t ip = 0, n = 0;
+  for (uint32_t shift = 0;; shift += 7) {
+    if (ip >= clen || shift > 28) return SB_EXTERNAL;
+    const uint32_t b = src[ip++];
+    n |= (b & 0x7fu) << shift;
+    if (!(b & 0x80u)) break;
+  }
+  if (n != dlen) return SB_EXTERNAL; // snap: BufferTooSmall when larger; a shorter block would leave rows undefined
+  uint32_t op = 0;
+  while (ip < clen) {
+    const uint32_t tag = src[ip++];
+    uint32_t len, offset;
+    if ((tag & 3u) == 0) {
+      len = (tag >> 2) + 1;
+      if (len > 60) {
+        const uint32_t nb = len - 60;
+        if (clen - ip < nb) return SB_EXTERNAL;
+        uint32_t l = 0;
+        for (uint32_t k = 0; k < nb; ++k) l |= uint32_t(src[ip + k]) << (8 * k);
+        ip += nb;
+        if (l == 0xffffffffu) return SB_EXTERNAL;
+        len = l + 1;
+      }
+      if (len > clen - ip || len > dlen - op) return SB_EXTERNAL;
+      for (uint32_t i = lane; i < len; i += 32) dst[op + i] = src[ip + i];
+      __syncwarp();
+      ip += len;
+      op += len;
+      continue;
+    }
+    if ((tag & 3u) == 1) {
+      if (ip >= clen) return SB_EXTERNAL;
+      len = 4 + ((tag >> 2) & 7u);
+      offset = ((tag >> 5) << 8) | src[ip++];
+    } else if ((tag & 3u) == 2) {
+      if (clen - ip < 2) return SB_EXTERNAL;
+      len = (tag >> 2) + 1;
+      offset = uint32_t(src[ip]) | (uint32_t(src[ip + 1]) << 8);
+      ip += 2;
+    } else {
+      if (clen - ip < 4) return SB_EXTERNAL;
+      len = (tag >> 2) + 1;
+      offset = uint32_t(src[ip]) | (uint32_t(src[ip + 1]) << 8) | (uint32_t(src[ip + 2]) << 16) | (uint32_t(src[ip + 3]) << 24);
+      ip += 4;
+    }
+    if (offset == 0 || offset > op || len > dlen - op) return SB_EXTERNAL;
+    // len <= 64; everything before op is final: an overlapping copy replicates the `offset` bytes before op
+    for (uint32_t i = lane; i < len; i += 32) {
+      const uint32_t b = dst[op - offset + (offset < len ? i % offset : i)];
+      dst[op + i] = uint8_t(b);
+    }
+    __syncwarp();
+    op += len;
+  }
+  return op == dlen ? 0 : SB_EXTERNAL;
+}
+__device__ __noinline__ bool dec_snappy_block(Dctx &cx, const uint8_t *src, uint32_t clen, uint8_t *dst, uint64_t out_bytes) {
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int rc = out_bytes > 0xffffffffull ? int(SB_EXTERNAL) : snappy_decode_warp(src, clen, dst, uint32_t(out_bytes));
+    if (threadIdx.x == 0) cx.bcast[0] = rc;
+  }
+  __syncthreads();
+  const int rc = cx.bcast[0];
+  __syncthreads();
+  if (rc) {
+    cx.flag(rc);
+    return false;
+  }
+  return true;
+}
+
 // Basic codecs (CommonCompression::decompress, basic.rs:62-72) into `dst`.
 __device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *src, uint32_t clen, uint8_t *dst,
                                           uint64_t out_bytes) {
@@ -122,7 +202,8 @@ __device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *sr
     return true;
   }
   if (codec == SB_C_LZ4) return dec_lz4_block(cx, src, clen, dst, out_bytes);
-  cx.flag(SB_NYI); // zstd / snappy pages: SURVEY §8 f3
+  if (codec == SB_C_SNAPPY) return dec_snappy_block(cx, src, clen, dst, out_bytes);
+  cx.flag(SB_NYI); // zstd pages: SURVEY §8 f3
   return false;
 }
 
@@ -889,7 +970,8 @@ __device__ bool decode_boolean(Dctx &cx, const uint8_t *src, uint32_t avail, uin
     emit_bits(dst_bitmap, dst_bit, n, bs);
     return true;
   }
-  case SB_C_LZ4: {
+  case SB_C_LZ4:
+  case SB_C_SNAPPY: {
     Arena mark = cx.ar;
     uint8_t *tmp = static_cast<uint8_t *>(cx.ar.alloc(uint64_t(nbytes) + 16));
     if (!tmp) {
@@ -913,8 +995,7 @@ __device__ bool decode_boolean(Dctx &cx, const uint8_t *src, uint32_t avail, uin
     emit_bits(dst_bitmap, dst_bit, n, bs);
     return true;
   }
-  case SB_C_ZSTD:
-  case SB_C_SNAPPY: cx.flag(SB_NYI); return false;
+  case SB_C_ZSTD: cx.flag(SB_NYI); return false;
   default: cx.flag(SB_OUT_OF_SPEC); return false;
   }
 }

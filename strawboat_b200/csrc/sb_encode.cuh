@@ -301,8 +301,48 @@ __device__ uint32_t lz4_emit_seq(uint8_t *out, uint32_t op, const uint8_t *lit, 
   __syncwarp();
   return q;
 }
+// Snappy raw elements for one (literal run, match) pair (basic.rs:138-152 -> snap::raw::Encoder; compressed bytes
+// are implementation defined, any valid stream decodes with snap::raw::Decoder): a literal element, then copy
+// elements with a 16-bit offset (1..64 bytes each; 11-bit form for 4..11 bytes at offsets < 2048).
+__device__ uint32_t snappy_emit_seq(uint8_t *out, uint32_t op, const uint8_t *lit, uint32_t nlit, uint32_t offset, uint32_t ml /*0: last*/) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t q = op;
+  if (nlit) {
+    const uint32_t l1 = nlit - 1;
+    const uint32_t nb = l1 < 60 ? 0u : l1 < (1u << 8) ? 1u : l1 < (1u << 16) ? 2u : l1 < (1u << 24) ? 3u : 4u;
+    if (lane == 0) {
+      out[q] = uint8_t(nb ? (59 + nb) << 2 : l1 << 2);
+      for (uint32_t k = 0; k < nb; ++k) out[q + 1 + k] = uint8_t(l1 >> (8 * k));
+    }
+    q += 1 + nb;
+    for (uint32_t i = lane; i < nlit; i += 32) out[q + i] = lit[i];
+    q += nlit;
+  }
+  // copy elements: their sizes are a pure function of (offset, ml), so every lane tracks q; lane 0 writes
+  for (uint32_t left = ml; left;) {
+    const uint32_t l = left > 64 ? (left - 64 < 4 ? 60u : 64u) : left;
+    if (l >= 4 && l <= 11 && offset < 2048) {
+      if (lane == 0) {
+        out[q] = uint8_t(1u | ((l - 4) << 2) | ((offset >> 8) << 5));
+        out[q + 1] = uint8_t(offset);
+      }
+      q += 2;
+    } else {
+      if (lane == 0) {
+        out[q] = uint8_t(2u | ((l - 1) << 2));
+        out[q + 1] = uint8_t(offset);
+        out[q + 2] = uint8_t(offset >> 8);
+      }
+      q += 3;
+    }
+    left -= l;
+  }
+  __syncwarp();
+  return q;
+}
 constexpr uint32_t kLz4HashBits = 12;
-__device__ uint32_t lz4_compress_cta(Dctx &cx, const uint8_t *in, uint32_t n, uint8_t *out) {
+// greedy matcher shared by the LZ4 and the Snappy writer (the element syntax is the only difference)
+template <bool SNAPPY> __device__ uint32_t lz_compress_cta(Dctx &cx, const uint8_t *in, uint32_t n, uint8_t *out) {
   Arena mark = cx.ar;
   uint32_t *tab = static_cast<uint32_t *>(cx.ar.alloc((1u << kLz4HashBits) * 4));
   if (!tab) {
@@ -314,6 +354,14 @@ __device__ uint32_t lz4_compress_cta(Dctx &cx, const uint8_t *in, uint32_t n, ui
   if (threadIdx.x < 32) {
     const uint32_t lane = threadIdx.x;
     uint32_t ip = 0, anchor = 0, op = 0;
+    if (SNAPPY) { // preamble: varint of the uncompressed length
+      uint32_t v = n;
+      do {
+        if (lane == 0) out[op] = uint8_t((v & 0x7fu) | (v >> 7 ? 0x80u : 0u));
+        ++op;
+        v >>= 7;
+      } while (v);
+    }
     const uint32_t mflimit = n >= 13 ? n - 12 : 0; // last match start (inclusive) -- LZ4 block end rules
     const uint32_t match_end_limit = n >= 5 ? n - 5 : 0;
     while (n >= 13 && ip <= mflimit) {
@@ -344,11 +392,11 @@ __device__ uint32_t lz4_compress_cta(Dctx &cx, const uint8_t *in, uint32_t n, ui
         ml += run;
         if (run < 32) break;
       }
-      op = lz4_emit_seq(out, op, in + anchor, mp - anchor, mp - mc, ml);
+      op = SNAPPY ? snappy_emit_seq(out, op, in + anchor, mp - anchor, mp - mc, ml) : lz4_emit_seq(out, op, in + anchor, mp - anchor, mp - mc, ml);
       ip = mp + ml;
       anchor = ip;
     }
-    op = lz4_emit_seq(out, op, in + anchor, n - anchor, 0, 0);
+    op = SNAPPY ? snappy_emit_seq(out, op, in + anchor, n - anchor, 0, 0) : lz4_emit_seq(out, op, in + anchor, n - anchor, 0, 0);
     if (lane == 0) cx.bcast[0] = int(op);
   }
   __syncthreads();
@@ -365,8 +413,9 @@ __device__ uint32_t enc_basic(Dctx &cx, int codec, const uint8_t *in, uint32_t n
     copy_bytes(out, in, n);
     return n;
   }
-  if (codec == SB_C_LZ4) return lz4_compress_cta(cx, in, n, out);
-  cx.flag(SB_NYI); // zstd / snappy writers: SURVEY §8 f3
+  if (codec == SB_C_LZ4) return lz_compress_cta<false>(cx, in, n, out);
+  if (codec == SB_C_SNAPPY) return lz_compress_cta<true>(cx, in, n, out);
+  cx.flag(SB_NYI); // zstd writer: SURVEY §8 f3
   return kEncFail;
 }
 

@@ -137,3 +137,22 @@ def test_roaring_portable_format():
     b = sbo.roaring_serialize(big)
     assert np.array_equal(sbo.roaring_deserialize(b), big)
     assert len(sbo.roaring_serialize(np.zeros(0, np.uint32))) == 8
+
+
+def test_snappy_raw_own_codec_vs_pyarrow():
+    """Snappy raw format (src/compression/basic.rs:98-105,138-152 -> snap::raw).  The oracle's encoder / decoder
+    are restated from the format description; pyarrow's snappy codec wraps Google's C++ library."""
+    pa = pytest.importorskip("pyarrow")
+    codec = pa.Codec("snappy")
+    rng = np.random.default_rng(5)
+    for data in corpus(rng):
+        comp = sbo.common_compress(sbo.C_SNAPPY, data)
+        assert sbo.common_decompress(sbo.C_SNAPPY, comp, len(data)) == data
+        if len(data):
+            assert codec.decompress(comp, decompressed_size=len(data)).to_pybytes() == data   # Google's decoder reads ours
+            comp2 = codec.compress(data).to_pybytes()
+            assert sbo.common_decompress(sbo.C_SNAPPY, comp2, len(data)) == data               # we read Google's
+    with pytest.raises(sbo.OracleError):
+        sbo.common_decompress(sbo.C_SNAPPY, sbo.common_compress(sbo.C_SNAPPY, b"abcdabcdabcd" * 10)[:-2], 120)
+    with pytest.raises(sbo.OracleError):
+        sbo.common_decompress(sbo.C_SNAPPY, sbo.common_compress(sbo.C_SNAPPY, b"abcdabcdabcd" * 10), 121)
