@@ -259,6 +259,34 @@ int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_col
                           const sb_write_options *opts, int32_t out_mem, sb_encoded_column *outs);
 void sb_release_encoded(sb_ctx *ctx, sb_encoded_column *outs, uint64_t n);
 
+/* ------------------------------------------------------------------------------------
+ * MULTI-GPU ENCODE: gather of the encoded column bodies on the writer rank
+ * ------------------------------------------------------------------------------------ */
+
+/* The reference writes a file from one process: NativeWriter::encode_chunk appends every column body at its
+ * absolute offset and finish() writes one footer (src/write/common.rs:71-119, src/write/writer.rs:128-167).  When
+ * the leaf columns of a chunk are encoded on several GPUs (leaf c on rank c mod world), this is the one exchange
+ * step: every rank learns the layout (ncclAllGather of sizes), the bodies travel once over NVLink (grouped
+ * ncclSend / ncclRecv) straight to their final position in the writer's staging buffer.  One process per GPU. */
+typedef struct sb_comm sb_comm;
+/* rank 0 makes the id (ncclGetUniqueId, 128 bytes) and hands it to the other ranks out of band */
+int32_t sb_comm_unique_id(uint8_t *id128);
+int32_t sb_comm_create(sb_ctx *ctx, int32_t rank, int32_t world, const uint8_t *id128, sb_comm **out);
+void sb_comm_destroy(sb_comm *comm);
+
+typedef struct {
+  uint64_t bytes_moved; /* bytes this rank sent (or, on the writer, received) over the interconnect */
+  uint64_t total_bytes; /* size of the gathered body region (all columns) */
+  float gather_ms;      /* CUDA-event time of the grouped send / recv on this rank */
+} sb_gather_stats;
+
+/* `local`: this rank's encoded columns (device resident), leaf order: local[k] is leaf rank + k * world.
+ * On the writer rank `outs` receives all n_total columns in leaf order: `bytes` point into one device buffer
+ * that holds the bodies back to back -- the file's body region -- and `metas` are the PageMeta records for the
+ * footer.  Release with sb_release_encoded(ctx, outs, n_total).  Collective: every rank must call it. */
+int32_t sb_gather_encoded(sb_ctx *ctx, sb_comm *comm, const sb_encoded_column *local, uint64_t n_local, uint64_t n_total, int32_t writer,
+                          sb_encoded_column *outs, sb_gather_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

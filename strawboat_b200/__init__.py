@@ -389,8 +389,8 @@ def _encode_columns(self, arrays, options=None, out="host"):
     if out == "host":
         _lib.sb_release_encoded(self._h, outs, n)
     else:
-        for r in res:
-            r._outs, r._n, r._ctx = outs, n, self
+        for i, r in enumerate(res):
+            r._outs, r._n, r._ctx, r._index = outs, n, self, i
     return res
 
 
@@ -412,6 +412,48 @@ def stat_page(type_, nullable, page, nested=None):
     d = {f: getattr(info, f) for f, _ in _capi.PageInfo._fields_ if f != "path"}
     d["path"] = [info.path[i] for i in range(min(info.depth, 4))]
     return tree.value.decode(), d
+
+
+def comm_unique_id():
+    """ncclGetUniqueId on the calling rank (rank 0 makes it and hands it to the others out of band)."""
+    buf = C.create_string_buffer(128)
+    rc = _lib.sb_comm_unique_id(buf)
+    if rc != _capi.SB_OK:
+        raise StrawboatError(rc, "sb_comm_unique_id: libnccl.so.2 could not be loaded")
+    return buf.raw
+
+
+class Comm:
+    """sb_comm: the NCCL communicator of the encode gather (one process per GPU; leaf c lives on rank c mod world)."""
+
+    def __init__(self, ctx, rank, world, unique_id):
+        h = C.c_void_p()
+        ctx._check(_lib.sb_comm_create(ctx._h, rank, world, unique_id, C.byref(h)))
+        self._h, self.ctx, self.rank, self.world = h, ctx, rank, world
+
+    def close(self):
+        if self._h:
+            _lib.sb_comm_destroy(self._h)
+            self._h = None
+
+    def gather_encoded(self, encoded, n_total, writer=0):
+        """Collective.  `encoded`: this rank's device-resident Encoded columns in leaf order (from
+        Context.encode_columns(..., out="device")).  Returns (list of Encoded in leaf order on the writer / None,
+        stats dict).  The writer's columns share one device buffer: the file's body region."""
+        n = len(encoded)
+        ins = (_capi.EncodedColumn * max(1, n))()
+        for i, e in enumerate(encoded):
+            ins[i] = e._outs[e._index] if getattr(e, "_outs", None) is not None else e._raw
+        outs = (_capi.EncodedColumn * max(1, n_total))() if self.rank == writer else None
+        st = _capi.GatherStats()
+        self.ctx._check(_lib.sb_gather_encoded(self.ctx._h, self._h, ins, n, n_total, writer, outs, C.byref(st)))
+        stats = {"bytes_moved": int(st.bytes_moved), "total_bytes": int(st.total_bytes), "gather_ms": float(st.gather_ms)}
+        if self.rank != writer:
+            return None, stats
+        res = [Encoded(outs[i]) for i in range(n_total)]
+        for i, r in enumerate(res):
+            r._outs, r._n, r._ctx, r._index = outs, n_total, self.ctx, i
+        return res, stats
 
 
 Context.encode_columns = _encode_columns

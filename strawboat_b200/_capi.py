@@ -73,10 +73,15 @@ class EncodedColumn(C.Structure):
                 ("n_pages", C.c_uint64), ("mem", C.c_int32), ("_owner", C.c_void_p)]
 
 
+class GatherStats(C.Structure):
+    _fields_ = [("bytes_moved", C.c_uint64), ("total_bytes", C.c_uint64), ("gather_ms", C.c_float)]
+
+
 # every symbol include/strawboat_b200.h declares
 EXPORTS = ["sb_ctx_create", "sb_ctx_destroy", "sb_ctx_set_stream", "sb_last_error", "sb_version",
            "sb_decode_columns", "sb_decode_pages", "sb_release_columns", "sb_last_stats",
-           "sb_encode_columns", "sb_release_encoded", "sb_stat_page"]
+           "sb_encode_columns", "sb_release_encoded", "sb_stat_page",
+           "sb_comm_unique_id", "sb_comm_create", "sb_comm_destroy", "sb_gather_encoded"]
 
 
 def load():
@@ -109,4 +114,13 @@ def load():
     L.sb_release_encoded.restype = None
     L.sb_stat_page.argtypes = [C.POINTER(Leaf), C.c_char_p, C.c_uint64, C.POINTER(PageInfo), C.c_char_p, C.c_uint64]
     L.sb_stat_page.restype = C.c_int32
+    L.sb_comm_unique_id.argtypes = [C.c_char_p]
+    L.sb_comm_unique_id.restype = C.c_int32
+    L.sb_comm_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.sb_comm_create.restype = C.c_int32
+    L.sb_comm_destroy.argtypes = [C.c_void_p]
+    L.sb_comm_destroy.restype = None
+    L.sb_gather_encoded.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(EncodedColumn), C.c_uint64, C.c_uint64, C.c_int32,
+                                    C.POINTER(EncodedColumn), C.POINTER(GatherStats)]
+    L.sb_gather_encoded.restype = C.c_int32
     return L

@@ -320,13 +320,6 @@ __global__ void sb_page_offsets_kernel(const EncPage *__restrict__ pages, const 
 
 using namespace sb;
 
-namespace {
-struct EncOwner {
-  void *dev = nullptr;
-  PinnedBlock pinned{nullptr, 0};
-  void *metas = nullptr;
-};
-} // namespace
 
 extern "C" {
 

@@ -25,6 +25,12 @@ struct Owner { // allocations handed to the caller through sb_column_out / sb_en
   std::vector<void *> host_malloc;
 };
 
+struct EncOwner { // what an sb_encoded_column owns (sb_encode_columns, sb_gather_encoded)
+  void *dev = nullptr;
+  PinnedBlock pinned{nullptr, 0};
+  void *metas = nullptr;
+};
+
 struct sb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, aux = nullptr;

@@ -87,3 +87,128 @@ def infer_schema_bytes(data):
 def column_body(data, column_meta):
     off, pages = column_meta
     return data[off:off + sum(p[0] for p in pages)]
+
+
+class NativeReader:
+    """Page iterator over one column body: read::reader::NativeReader (src/read/reader.rs:45-145).
+    `source` is the whole file (bytes-like) or any seekable binary reader positioned anywhere; `column_meta` =
+    (offset, [(length, num_values)]) from read_meta.  next() / nth(n) yield (num_values, page bytes) -- the items
+    column_iter_to_arrays consumes (src/read/deserialize.rs:237-245); skip_page() and nth() seek over the skipped
+    pages without reading them (reader.rs:91-116,136-145)."""
+
+    def __init__(self, source, column_meta):
+        self.offset, self.page_metas = column_meta[0], list(column_meta[1])
+        self.current_page = 0
+        self._pos = self.offset
+        self._src = source
+        self._file = hasattr(source, "read") and hasattr(source, "seek")
+        self._scratch = None
+
+    def has_next(self):
+        return self.current_page < len(self.page_metas)
+
+    def swap_buffer(self, scratch):
+        """PageIterator::swap_buffer (src/read/mod.rs:55-57): hand a page buffer back for reuse"""
+        self._scratch, scratch = scratch, self._scratch
+        return scratch
+
+    def _read(self, n):
+        if self._file:
+            self._src.seek(self._pos)
+            buf = self._src.read(n)
+        else:
+            buf = bytes(self._src[self._pos:self._pos + n])
+        if len(buf) != n:
+            raise EOFError("failed to fill whole buffer")
+        self._pos += n
+        return buf
+
+    def next(self):
+        if not self.has_next():
+            return None
+        length, num_values = self.page_metas[self.current_page]
+        buf = self._read(length)
+        self.current_page += 1
+        return num_values, buf
+
+    def nth(self, n):
+        """the next n-th page, skipping the pages in between (Iterator::nth)"""
+        skipped, length = 0, 0
+        while skipped < n:
+            if self.current_page == len(self.page_metas):
+                return None
+            length += self.page_metas[self.current_page][0]
+            self.current_page += 1
+            skipped += 1
+        self._pos += length
+        return self.next()
+
+    def skip_page(self):
+        if self.has_next():
+            self._pos += self.page_metas[self.current_page][0]
+            self.current_page += 1
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        item = self.next()
+        if item is None:
+            raise StopIteration
+        return item
+
+
+class NativeWriter:
+    """write::NativeWriter (src/write/writer.rs:42-173) over the GPU page encoder: start() writes the header,
+    write(chunk) encodes every leaf of a chunk page by page (encode_chunk, src/write/common.rs:49-119 ->
+    Context.encode_columns) and appends the column bodies, finish() writes schema + ColumnMeta footer.
+    `chunk` = list of strawboat_b200.LeafArray in leaf order (what to_leaves / to_nested yield for the chunk)."""
+
+    def __init__(self, ctx, sink, schema_bytes=b"", options=None):
+        self.ctx, self.sink, self.options = ctx, sink, options
+        self.schema_bytes = schema_bytes if isinstance(schema_bytes, (bytes, bytearray)) else schema_to_bytes(schema_bytes)
+        self.metas = []            # pub metas: Vec<ColumnMeta> (writer.rs:56)
+        self.offset = 0
+        self.started = self.finished = False
+
+    def start(self):
+        self.sink.write(MAGIC + b"\0\0")
+        self.offset = 8
+        self.started = True
+
+    def write(self, chunk):
+        if not self.started:
+            raise RuntimeError("start must be called before written")  # writer.rs:110-114
+        for enc in self.ctx.encode_columns(list(chunk), self.options):
+            self.write_encoded(enc.data, enc.metas)
+
+    def write_encoded(self, body, pages):
+        """append one already encoded column body (the multi-GPU writer rank feeds gathered bodies through here)"""
+        self.metas.append((self.offset, list(pages)))
+        self.sink.write(body)
+        self.offset += len(body)
+
+    def finish(self):
+        if not self.started:
+            raise RuntimeError("start must be called before finish")
+        meta = bytearray(struct.pack("<Q", len(self.metas)))
+        for off, pages in self.metas:
+            meta += struct.pack("<QQ", off, len(pages))
+            for length, num_values in pages:
+                meta += struct.pack("<QQ", length, num_values)
+        self.sink.write(self.schema_bytes)
+        self.sink.write(bytes(meta))
+        self.sink.write(struct.pack("<II", len(self.schema_bytes), len(meta)))
+        self.sink.write(CONTINUATION + b"\0\0\0\0")
+        self.finished = True
+        return self.offset + len(self.schema_bytes) + len(meta) + 16
+
+
+def read_columns(ctx, data, leaves):
+    """batch_read_array over every column of a file: `leaves` = [(type, nullable[, nested])] per ColumnMeta.
+    Returns the decoded columns (host)."""
+    import strawboat_b200 as sb
+    cols = []
+    for cm, lf in zip(read_meta(data), leaves):
+        cols.append(sb.Column(lf[0], lf[1], column_body(data, cm), cm[1], lf[2] if len(lf) > 2 else None))
+    return ctx.decode_columns(cols)
