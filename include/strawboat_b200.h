@@ -260,6 +260,87 @@ int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_col
 void sb_release_encoded(sb_ctx *ctx, sb_encoded_column *outs, uint64_t n);
 
 /* ------------------------------------------------------------------------------------
+ * NESTED ASSEMBLY + ARROW C DATA INTERFACE EXPORT (read side of nested columns; ownership)
+ * ------------------------------------------------------------------------------------ */
+
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+/* The Arrow C Data Interface (arrow.apache.org/docs/format/CDataInterface.html), ABI-stable definitions */
+struct ArrowSchema {
+  const char *format;
+  const char *name;
+  const char *metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema **children;
+  struct ArrowSchema *dictionary;
+  void (*release)(struct ArrowSchema *);
+  void *private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void **buffers;
+  struct ArrowArray **children;
+  struct ArrowArray *dictionary;
+  void (*release)(struct ArrowArray *);
+  void *private_data;
+};
+#endif
+
+/* The Field / DataType tree of one column (what column_iter_to_arrays / batch_read_array receive as `field`,
+ * src/read/deserialize.rs:237-245, src/read/batch_read.rs:190-196). */
+typedef struct sb_field {
+  int32_t kind;      /* SB_N_PRIMITIVE (leaf) / SB_N_LIST / SB_N_STRUCT */
+  int32_t type;      /* leaf: SB_* physical type */
+  int32_t utf8;      /* leaf SB_BINARY / SB_LARGE_BINARY: export as Utf8 / LargeUtf8 */
+  int32_t nullable;
+  int32_t large;     /* SB_N_LIST: LargeList (i64 offsets) */
+  int32_t n_children;
+  const struct sb_field *children;
+  const char *name;
+} sb_field;
+
+/* Replaces the array construction of the readers: create_list / create_struct over the NestedState of the first
+ * leaf (src/read/array/list.rs, struct_.rs; src/read/batch_read.rs:66-187) and PrimitiveArray / BinaryArray /
+ * BooleanArray::try_new (src/read/array/integer.rs:86 ...).  `leaves`: the decoded leaves of the field, in leaf
+ * order, all from one sb_decode_columns / sb_decode_pages call.  Nothing is copied (List<i32> offsets are narrowed
+ * from the i64 NestedState offsets, as create_list does).  OWNERSHIP MOVES: the leaves are zeroed and their buffers
+ * live until out_array->release is called (which returns them to `ctx`, so the context must outlive the array).
+ * Buffers are host pointers for out_mem = SB_MEM_HOST; for SB_MEM_DEVICE wrap the result in an ArrowDeviceArray
+ * {array, device_id, ARROW_DEVICE_CUDA}. */
+int32_t sb_export_arrow(sb_ctx *ctx, const sb_field *field, sb_column_out *leaves, uint64_t n_leaves, struct ArrowArray *out_array,
+                        struct ArrowSchema *out_schema);
+
+/* ------------------------------------------------------------------------------------
+ * NESTED LEVELS from Arrow buffers (write side of nested columns)
+ * ------------------------------------------------------------------------------------ */
+
+/* One depth of a nested leaf, root -> leaf: what arrow2's to_nested() yields per leaf (Nested::{List, LargeList,
+ * Struct, Primitive}; call site src/write/common.rs:66-68).  Lists must be compact (children in order, a null
+ * list has none). */
+typedef struct {
+  int32_t kind;            /* SB_N_LIST / SB_N_STRUCT / SB_N_PRIMITIVE */
+  int32_t nullable;
+  const void *offsets;     /* SB_N_LIST: length + 1 offsets */
+  int32_t offset_width;    /* 4 (List) or 8 (LargeList) */
+  const uint8_t *validity; /* LSB-first bitmap, NULL = all valid */
+  uint64_t length;         /* elements at this depth */
+} sb_nested_level;
+
+/* Replaces arrow2's write_rep_and_def iteration (src/write/serialize.rs:217-232): the Dremel (rep, def) levels of
+ * one leaf, generated on the device from the Arrow offsets / validity buffers of its ancestors.  `mem` says where
+ * the input buffers live; the level arrays are DEVICE memory owned by the caller (sb_free_device) and can be
+ * passed straight to sb_encode_columns (sb_leaf_array.rep_levels / def_levels with mem = SB_MEM_DEVICE).
+ * n_slots = leaf slots the levels describe (sb_leaf_array.length), n_levels = level entries. */
+int32_t sb_nested_levels(sb_ctx *ctx, const sb_nested_level *path, int32_t n_depths, int32_t mem, uint32_t **rep_levels, uint32_t **def_levels,
+                         uint64_t *n_levels, uint64_t *n_slots);
+void sb_free_device(sb_ctx *ctx, void *p);
+
+/* ------------------------------------------------------------------------------------
  * MULTI-GPU ENCODE: gather of the encoded column bodies on the writer rank
  * ------------------------------------------------------------------------------------ */
 

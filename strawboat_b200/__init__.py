@@ -414,6 +414,102 @@ def stat_page(type_, nullable, page, nested=None):
     return tree.value.decode(), d
 
 
+class DeviceLevels:
+    """Dremel levels generated on the device (sb_nested_levels): quacks like a CUDA uint32 tensor for LeafArray."""
+
+    def __init__(self, ctx, ptr, n):
+        self._ctx, self._ptr, self._n = ctx, ptr, n
+
+    def data_ptr(self):
+        return self._ptr
+
+    def numel(self):
+        return self._n
+
+    def free(self):
+        if self._ptr and self._ctx._h:
+            _lib.sb_free_device(self._ctx._h, C.c_void_p(self._ptr))
+        self._ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _nested_levels(self, path):
+    """arrow2's write_rep_and_def over the `Nested` descriptors of one leaf, on the device.
+    path: root -> leaf list of dicts {kind, nullable, length, offsets (int32 / int64 ndarray or CUDA tensor, lists),
+    validity (bool ndarray / packed CUDA uint8 tensor / None)}.  Returns (rep, def, n_slots): DeviceLevels usable as
+    LeafArray(rep_levels=, def_levels=)."""
+    n = len(path)
+    lv = (_capi.NestedLevel * n)()
+    keep, mem = [], None
+    for i, d in enumerate(path):
+        lv[i].kind, lv[i].nullable, lv[i].length = d["kind"], int(bool(d.get("nullable"))), int(d["length"])
+        for name in ("offsets", "validity"):
+            a = d.get(name)
+            if a is None:
+                continue
+            if hasattr(a, "data_ptr"):
+                m, ptr = MEM_DEVICE, a.data_ptr()
+                if name == "offsets":
+                    lv[i].offset_width = a.element_size()
+            else:
+                m = MEM_HOST
+                if name == "validity":
+                    a = np.packbits(np.asarray(a, dtype=bool), bitorder="little")
+                else:
+                    a = np.ascontiguousarray(a)
+                    assert a.dtype in (np.int32, np.int64)
+                    lv[i].offset_width = a.dtype.itemsize
+                ptr = a.ctypes.data if a.size else 0
+            keep.append(a)
+            assert mem in (None, m), "all nested buffers must live in the same memory space"
+            mem = m
+            setattr(lv[i], name, ptr)
+    rep, de = C.c_void_p(), C.c_void_p()
+    nl, ns = C.c_uint64(), C.c_uint64()
+    self._check(_lib.sb_nested_levels(self._h, lv, n, MEM_HOST if mem is None else mem, C.byref(rep), C.byref(de), C.byref(nl), C.byref(ns)))
+    return DeviceLevels(self, rep.value, nl.value), DeviceLevels(self, de.value, nl.value), int(ns.value)
+
+
+def make_field(kind, type_=NULL, nullable=False, children=(), name="", utf8=False, large=False):
+    """sb_field tree (the Field the reference's readers receive).  Keeps its children alive."""
+    f = _capi.Field()
+    f.kind, f.type, f.utf8, f.nullable, f.large = kind, type_, int(utf8), int(bool(nullable)), int(large)
+    f.name = name.encode()
+    if children:
+        arr = (_capi.Field * len(children))(*children)
+        f.n_children = len(children)
+        f.children = C.cast(arr, C.POINTER(_capi.Field))
+        f._keep = (arr, children)
+    return f
+
+
+def _read_arrow(self, columns, field):
+    """batch_read_array + create_list / create_struct: decode the leaves of one field and assemble them into ONE
+    Arrow array handed out through the C Data Interface (imported here with pyarrow; host buffers, zero copy).  The
+    array's buffers go back to this context when the last reference to it dies: keep the context alive."""
+    import pyarrow as pa
+    n = len(columns)
+    ins, keep = self._marshal(columns)
+    outs = (_capi.ColumnOut * n)()
+    rc = _lib.sb_decode_columns(self._h, ins, n, MEM_HOST, outs)
+    if rc != _capi.SB_OK:
+        msg = _lib.sb_last_error(self._h).decode()
+        _lib.sb_release_columns(self._h, outs, n)
+        raise StrawboatError(rc, msg)
+    arr, sch = _capi.ArrowArray(), _capi.ArrowSchema()
+    rc = _lib.sb_export_arrow(self._h, C.byref(field), outs, n, C.byref(arr), C.byref(sch))
+    if rc != _capi.SB_OK:
+        msg = _lib.sb_last_error(self._h).decode()
+        _lib.sb_release_columns(self._h, outs, n)
+        raise StrawboatError(rc, msg)
+    return pa.Array._import_from_c(C.addressof(arr), C.addressof(sch))
+
+
 def comm_unique_id():
     """ncclGetUniqueId on the calling rank (rank 0 makes it and hands it to the others out of band)."""
     buf = C.create_string_buffer(128)
@@ -458,3 +554,5 @@ class Comm:
 
 Context.encode_columns = _encode_columns
 Context.release_encoded = _release_encoded
+Context.nested_levels = _nested_levels
+Context.read_arrow = _read_arrow

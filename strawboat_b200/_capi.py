@@ -77,11 +77,35 @@ class GatherStats(C.Structure):
     _fields_ = [("bytes_moved", C.c_uint64), ("total_bytes", C.c_uint64), ("gather_ms", C.c_float)]
 
 
+class NestedLevel(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("nullable", C.c_int32), ("offsets", C.c_void_p), ("offset_width", C.c_int32),
+                ("validity", C.c_void_p), ("length", C.c_uint64)]
+
+
+class Field(C.Structure):
+    pass
+
+
+Field._fields_ = [("kind", C.c_int32), ("type", C.c_int32), ("utf8", C.c_int32), ("nullable", C.c_int32), ("large", C.c_int32),
+                  ("n_children", C.c_int32), ("children", C.POINTER(Field)), ("name", C.c_char_p)]
+
+
+class ArrowSchema(C.Structure):
+    _fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64), ("n_children", C.c_int64),
+                ("children", C.c_void_p), ("dictionary", C.c_void_p), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class ArrowArray(C.Structure):
+    _fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64), ("n_children", C.c_int64),
+                ("buffers", C.c_void_p), ("children", C.c_void_p), ("dictionary", C.c_void_p), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
 # every symbol include/strawboat_b200.h declares
 EXPORTS = ["sb_ctx_create", "sb_ctx_destroy", "sb_ctx_set_stream", "sb_last_error", "sb_version",
            "sb_decode_columns", "sb_decode_pages", "sb_release_columns", "sb_last_stats",
            "sb_encode_columns", "sb_release_encoded", "sb_stat_page",
-           "sb_comm_unique_id", "sb_comm_create", "sb_comm_destroy", "sb_gather_encoded"]
+           "sb_comm_unique_id", "sb_comm_create", "sb_comm_destroy", "sb_gather_encoded",
+           "sb_nested_levels", "sb_free_device", "sb_export_arrow"]
 
 
 def load():
@@ -123,4 +147,11 @@ def load():
     L.sb_gather_encoded.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(EncodedColumn), C.c_uint64, C.c_uint64, C.c_int32,
                                     C.POINTER(EncodedColumn), C.POINTER(GatherStats)]
     L.sb_gather_encoded.restype = C.c_int32
+    L.sb_nested_levels.argtypes = [C.c_void_p, C.POINTER(NestedLevel), C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.sb_nested_levels.restype = C.c_int32
+    L.sb_free_device.argtypes = [C.c_void_p, C.c_void_p]
+    L.sb_free_device.restype = None
+    L.sb_export_arrow.argtypes = [C.c_void_p, C.POINTER(Field), C.POINTER(ColumnOut), C.c_uint64, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
+    L.sb_export_arrow.restype = C.c_int32
     return L

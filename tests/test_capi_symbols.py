@@ -51,7 +51,8 @@ def test_ctypes_mirror_matches_the_header(tmp_path):
     from strawboat_b200 import _capi
     structs = {"sb_page_meta": _capi.PageMeta, "sb_leaf": _capi.Leaf, "sb_column_in": _capi.ColumnIn, "sb_column_out": _capi.ColumnOut,
                "sb_stats": _capi.Stats, "sb_write_options": _capi.WriteOptions, "sb_leaf_array": _capi.LeafArray,
-               "sb_encoded_column": _capi.EncodedColumn, "sb_page_info": _capi.PageInfo, "sb_gather_stats": _capi.GatherStats}
+               "sb_encoded_column": _capi.EncodedColumn, "sb_page_info": _capi.PageInfo, "sb_gather_stats": _capi.GatherStats, "sb_nested_level": _capi.NestedLevel,
+               "sb_field": _capi.Field, "struct ArrowArray": _capi.ArrowArray, "struct ArrowSchema": _capi.ArrowSchema}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "strawboat_b200.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
@@ -62,7 +63,7 @@ def test_ctypes_mirror_matches_the_header(tmp_path):
     src.write_text("\n".join(lines))
     exe = tmp_path / "abi"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
-    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    got = dict(line.rsplit(None, 1) for line in subprocess.check_output([str(exe)], text=True).splitlines())
     for cname, cls in structs.items():
         assert int(got[cname]) == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
