@@ -193,6 +193,7 @@ __device__ bool binary_page_size(Dctx &cx, const uint8_t *page, uint32_t page_le
   switch (b.codec) {
   case SB_C_NONE:
   case SB_C_LZ4:
+  case SB_C_ZSTD:
   case SB_C_SNAPPY: { // second hdr9 carries the value bytes (binary/mod.rs:147,159)
     if (b.body_avail - b.compressed < 9) {
       cx.flag(SB_IO);
@@ -205,7 +206,6 @@ __device__ bool binary_page_size(Dctx &cx, const uint8_t *page, uint32_t page_le
       *val_pos = body_pos + b.compressed + 9;
     return true;
   }
-  case SB_C_ZSTD: cx.flag(SB_NYI); return false;
   case SB_C_ONEVALUE: { // binary/one_value.rs:71-99
     if (b.body_avail < 4) {
       cx.flag(SB_IO);
@@ -418,6 +418,7 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
   switch (b.codec) {
   case SB_C_NONE:
   case SB_C_LZ4:
+  case SB_C_ZSTD:
   case SB_C_SNAPPY: { // Basic: hdr9(offsets) + hdr9(values) through the same common codec (mod.rs:120-173)
     const uint64_t obytes = uint64_t(n + 1) * OW;
     const uint8_t *raw = b.body;
@@ -483,7 +484,6 @@ __device__ bool decode_binary(Dctx &cx, const uint8_t *page, uint32_t page_len, 
     if (values_tiled && b.codec == SB_C_NONE && c2 == u2) return true; // value bytes: tiles 1.. of this page
     return dec_basic(cx, b.codec, h2 + 9, c2, out_val, u2);
   }
-  case SB_C_ZSTD: cx.flag(SB_NYI); return false;
   case SB_C_ONEVALUE: {
     if (b.body_avail < 4) {
       cx.flag(SB_IO);

@@ -12,6 +12,7 @@
 #pragma once
 #include "sb_common.cuh"
 #include "sb_lz4.cuh"
+#include "sb_zstd.cuh"
 
 namespace sb {
 
@@ -190,6 +191,32 @@ __device__ __noinline__ bool dec_snappy_block(Dctx &cx, const uint8_t *src, uint
   return true;
 }
 
+// Zstandard frame (basic.rs:93-97): warp 0 of the CTA, tables from the arena, literals in the global scratch
+__device__ __noinline__ bool dec_zstd_block(Dctx &cx, const uint8_t *src, uint32_t clen, uint8_t *dst, uint64_t out_bytes) {
+  Arena mark = cx.ar;
+  ZstdTables *T = static_cast<ZstdTables *>(cx.ar.alloc(sizeof(ZstdTables)));
+  uint8_t *lits = static_cast<uint8_t *>(cx.ar.alloc_global(min(out_bytes, uint64_t(128u << 10)) + 32));
+  if (!T || !lits || out_bytes > 0xffffffffull) {
+    cx.ar = mark;
+    cx.flag(SB_NYI);
+    return false;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int rc = zstd_decode_warp(src, clen, dst, uint32_t(out_bytes), T, lits);
+    if (threadIdx.x == 0) cx.bcast[0] = rc;
+  }
+  __syncthreads();
+  const int rc = cx.bcast[0];
+  __syncthreads();
+  cx.ar = mark;
+  if (rc) {
+    cx.flag(rc);
+    return false;
+  }
+  return true;
+}
+
 // Basic codecs (CommonCompression::decompress, basic.rs:62-72) into `dst`.
 __device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *src, uint32_t clen, uint8_t *dst,
                                           uint64_t out_bytes) {
@@ -203,7 +230,8 @@ __device__ __forceinline__ bool dec_basic(Dctx &cx, int codec, const uint8_t *sr
   }
   if (codec == SB_C_LZ4) return dec_lz4_block(cx, src, clen, dst, out_bytes);
   if (codec == SB_C_SNAPPY) return dec_snappy_block(cx, src, clen, dst, out_bytes);
-  cx.flag(SB_NYI); // zstd pages: SURVEY §8 f3
+  if (codec == SB_C_ZSTD) return dec_zstd_block(cx, src, clen, dst, out_bytes);
+  cx.flag(SB_OUT_OF_SPEC);
   return false;
 }
 
@@ -971,6 +999,7 @@ __device__ bool decode_boolean(Dctx &cx, const uint8_t *src, uint32_t avail, uin
     return true;
   }
   case SB_C_LZ4:
+  case SB_C_ZSTD:
   case SB_C_SNAPPY: {
     Arena mark = cx.ar;
     uint8_t *tmp = static_cast<uint8_t *>(cx.ar.alloc(uint64_t(nbytes) + 16));
@@ -995,7 +1024,6 @@ __device__ bool decode_boolean(Dctx &cx, const uint8_t *src, uint32_t avail, uin
     emit_bits(dst_bitmap, dst_bit, n, bs);
     return true;
   }
-  case SB_C_ZSTD: cx.flag(SB_NYI); return false;
   default: cx.flag(SB_OUT_OF_SPEC); return false;
   }
 }

@@ -341,9 +341,8 @@ int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_col
                           sb_encoded_column *outs) {
   if (!ctx) return SB_CUDA;
   if (!cols || !outs || !opts || (out_mem != SB_MEM_HOST && out_mem != SB_MEM_DEVICE)) return fail(ctx, SB_INVALID_ARG, "bad arguments");
-  if (opts->default_compression == SB_C_ZSTD)
-    return fail(ctx, SB_NYI, "the zstd page writer is not implemented (SURVEY 8 f3)");
-  if (opts->default_compression != SB_C_NONE && opts->default_compression != SB_C_LZ4 && opts->default_compression != SB_C_SNAPPY)
+  if (opts->default_compression != SB_C_NONE && opts->default_compression != SB_C_LZ4 && opts->default_compression != SB_C_SNAPPY &&
+      opts->default_compression != SB_C_ZSTD)
     return fail(ctx, SB_OUT_OF_SPEC, "default_compression must be a common codec (None / LZ4 / Zstd / Snappy)");
   SB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;

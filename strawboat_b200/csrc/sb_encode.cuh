@@ -415,7 +415,26 @@ __device__ uint32_t enc_basic(Dctx &cx, int codec, const uint8_t *in, uint32_t n
   }
   if (codec == SB_C_LZ4) return lz_compress_cta<false>(cx, in, n, out);
   if (codec == SB_C_SNAPPY) return lz_compress_cta<true>(cx, in, n, out);
-  cx.flag(SB_NYI); // zstd writer: SURVEY §8 f3
+  if (codec == SB_C_ZSTD) {
+    // A valid Zstandard frame that any decoder (zstd::bulk::decompress_to_buffer, basic.rs:93-97) reads: single
+    // segment, 4-byte frame content size, RAW blocks of at most 128 KiB (RFC 8878 3.1.1.2.2).  Stored, not
+    // compressed: the entropy coder (FSE / Huffman writer) is not part of this build -- pages still shrink through
+    // the adaptive codecs above the common codec; files are readable by the reference, only larger than libzstd's.
+    constexpr uint32_t BLK = 128u << 10;
+    const uint32_t nblk = n ? (n + BLK - 1) / BLK : 1;
+    if (threadIdx.x == 0) {
+      out[0] = 0x28, out[1] = 0xB5, out[2] = 0x2F, out[3] = 0xFD;
+      out[4] = 0xA0; // FCS flag 2 (4 bytes), single segment, no checksum, no dictionary
+      st_le(out + 5, n, 4);
+      for (uint32_t b = 0; b < nblk; ++b) {
+        const uint32_t sz = min(BLK, n - b * BLK);
+        st_le(out + 9 + uint64_t(b) * (BLK + 3), (sz << 3) | (b + 1 == nblk ? 1u : 0u), 3);
+      }
+    }
+    for (uint32_t b = 0; b < nblk; ++b) copy_bytes(out + 9 + uint64_t(b) * (BLK + 3) + 3, in + uint64_t(b) * BLK, min(BLK, n - b * BLK));
+    return 9 + 3 * nblk + n;
+  }
+  cx.flag(SB_OUT_OF_SPEC);
   return kEncFail;
 }
 
