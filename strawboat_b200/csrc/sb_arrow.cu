@@ -154,6 +154,20 @@ int build_array(sb_ctx *ctx, const sb_field *f, const sb_column_out *leaves, uin
     if (f->n_children != 1) return SB_INVALID_ARG;
     const uint64_t len = first.nested_len[depth];
     const int64_t *off64 = first.nested_offsets[depth];
+    if (!off64 && len == 0) { // a column without pages: no NestedState was ever built -- an empty list array has offsets [0]
+      if (first.mem == SB_MEM_HOST) {
+        void *z = std::calloc(1, 16);
+        if (!z) return SB_CUDA;
+        p->host_allocs.push_back(z);
+        off64 = static_cast<const int64_t *>(z);
+      } else {
+        void *z = nullptr;
+        cudaSetDevice(ctx->device);
+        if (cudaMallocAsync(&z, 16, ctx->stream) != cudaSuccess || cudaMemsetAsync(z, 0, 16, ctx->stream) != cudaSuccess) return SB_CUDA;
+        p->dev_allocs.push_back(z);
+        off64 = static_cast<const int64_t *>(z);
+      }
+    }
     if (!off64) return SB_INVALID_ARG;
     out->length = int64_t(len);
     p->buffers.push_back(first.nested_validity[depth]);
