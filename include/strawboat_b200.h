@@ -160,6 +160,51 @@ int32_t sb_decode_pages(sb_ctx *ctx, const sb_column_in *pages, uint64_t n_pages
 
 void sb_release_columns(sb_ctx *ctx, sb_column_out *outs, uint64_t n);
 
+/* ---- ownership and overlap: the rest of the reader boundary (SURVEY §8b "Ownership") ----------------------
+ * The reference moves freshly allocated Vec<T> / MutableBitmap into arrow2 Buffers (src/read/array/integer.rs:86)
+ * and recycles page buffers through PageIterator::swap_buffer (src/read/mod.rs:55-57).  Here the caller may own
+ * the output memory instead (plan -> allocate -> run), and a call may be left in flight while the host prepares
+ * the next one. */
+
+/* Caller-owned output buffers of one FLAT column (nested leaves stay library-allocated: their NestedState sizes
+ * are only known after the level pass).  A NULL pointer = let the library allocate that buffer.  With
+ * out_mem = SB_MEM_DEVICE the pointers are device memory, 16-byte aligned, and the decoders write into them
+ * directly; with SB_MEM_HOST they are host memory (pinned, to keep the copy asynchronous) filled by the D2H copy.
+ * Buffers handed in are never freed by sb_release_columns. */
+typedef struct {
+  void *values;
+  uint64_t values_cap;
+  void *offsets;
+  uint64_t offsets_cap;
+  uint8_t *validity;
+  uint64_t validity_cap; /* bitmaps are written in 4-byte words: round the capacity up to a multiple of 4 */
+} sb_out_buffers;
+
+/* Buffer sizes of every column: exact, including the data-dependent value bytes of binary / utf8 columns (runs
+ * the size pass over their pages) and the leaf slots of nested leaves. */
+typedef struct {
+  uint64_t length;
+  uint64_t values_bytes;
+  uint64_t offsets_bytes;
+  uint64_t validity_bytes;
+} sb_column_sizes;
+int32_t sb_plan_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, sb_column_sizes *sizes);
+
+/* sb_decode_columns into caller-owned buffers (`bufs`: n_cols entries, or NULL). */
+int32_t sb_decode_columns_into(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, int32_t out_mem, const sb_out_buffers *bufs,
+                               sb_column_out *outs);
+
+/* Asynchronous form: submits every copy and kernel of the call on the context's stream and returns.  `cols`, the
+ * page bytes, `bufs` and `outs` must stay valid until sb_decode_wait(ctx), which blocks until the work is done,
+ * fills page_status / statistics and returns what sb_decode_columns would have returned.  One call may be in
+ * flight per context (submitting another one, or encoding, collects it first); several contexts driven by one host
+ * thread overlap their H2D copies, kernels and D2H copies.  Binary / nested columns still block inside the submit
+ * for their size pass.  sb_decode_ready: 1 when sb_decode_wait would not block. */
+int32_t sb_decode_columns_async(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, int32_t out_mem, const sb_out_buffers *bufs,
+                                sb_column_out *outs);
+int32_t sb_decode_wait(sb_ctx *ctx);
+int32_t sb_decode_ready(sb_ctx *ctx);
+
 /* Counters of the last decode/encode call on this context. */
 typedef struct {
   uint64_t pages;
@@ -168,10 +213,11 @@ typedef struct {
   uint64_t kernel_launches;
   float device_ms;         /* CUDA-event time of the kernels of the last call */
   uint64_t codec_pages[32]; /* pages per top-level codec id */
-  float main_kernel_ms;    /* decode: sb_decode_kernel (pass 1) alone */
+  float main_kernel_ms;    /* decode: sb_decode_kernel (pass 1: binary, boolean, nested, LZ4-in-tree, Freq, Patas pages) alone */
   float lz4_kernel_ms;     /* decode: sb_lz4_kernel alone (runs concurrently with the main kernel) */
   uint64_t lz4_bytes;      /* decode: compressed + decoded bytes of the blocks sb_lz4_kernel handled */
   float host_ms;           /* wall time of the whole call on the host */
+  float light_kernel_ms;   /* decode: sb_decode_light_kernel alone (flat fixed-width pages with light codec trees; concurrent) */
 } sb_stats;
 int32_t sb_last_stats(const sb_ctx *ctx, sb_stats *out);
 

@@ -195,7 +195,7 @@ class Context:
         self._check(_lib.sb_last_stats(self._h, C.byref(s)))
         return {"pages": s.pages, "bytes_in": s.bytes_in, "bytes_out": s.bytes_out,
                 "kernel_launches": s.kernel_launches, "device_ms": s.device_ms,
-                "main_kernel_ms": s.main_kernel_ms, "lz4_kernel_ms": s.lz4_kernel_ms,
+                "main_kernel_ms": s.main_kernel_ms, "lz4_kernel_ms": s.lz4_kernel_ms, "light_kernel_ms": s.light_kernel_ms,
                 "lz4_bytes": s.lz4_bytes, "host_ms": s.host_ms,
                 "codec_pages": {i: s.codec_pages[i] for i in range(32) if s.codec_pages[i]}}
 
@@ -233,6 +233,71 @@ class Context:
         if out == "host" and copy:
             group.release()
         return res
+
+    # ---- plan -> allocate -> run, and the asynchronous form --------------------------------------------------
+    def plan_columns(self, columns):
+        """sb_plan_columns: exact buffer sizes of every column (runs the size pass for binary / nested leaves)"""
+        n = len(columns)
+        ins, keep = self._marshal(columns)
+        sizes = (_capi.ColumnSizes * n)()
+        self._check(_lib.sb_plan_columns(self._h, ins, n, sizes))
+        return [{"length": int(s.length), "values_bytes": int(s.values_bytes), "offsets_bytes": int(s.offsets_bytes),
+                 "validity_bytes": int(s.validity_bytes)} for s in sizes]
+
+    @staticmethod
+    def _out_buffers(bufs, n):
+        """bufs: per column None or a dict {values, offsets, validity} of writable uint8 buffers (CUDA tensors for
+        out="device", pinned / ordinary numpy arrays for out="host")"""
+        if bufs is None:
+            return None, []
+        arr, keep = (_capi.OutBuffers * n)(), []
+        for i, b in enumerate(bufs):
+            for name in ("values", "offsets", "validity"):
+                a = (b or {}).get(name)
+                if a is None:
+                    continue
+                keep.append(a)
+                if hasattr(a, "data_ptr"):
+                    ptr, cap = a.data_ptr(), a.numel() * a.element_size()
+                else:
+                    ptr, cap = a.ctypes.data, a.nbytes
+                setattr(arr[i], name, ptr)
+                setattr(arr[i], name + "_cap", cap)
+        return arr, keep
+
+    def decode_columns_async(self, columns, out="host", bufs=None, copy=False):
+        """sb_decode_columns_async: returns a handle; handle.wait() -> the decoded columns (as decode_columns).
+        Several contexts driven from one thread overlap their copies and kernels."""
+        n = len(columns)
+        ins, keep = self._marshal(columns)
+        outs = (_capi.ColumnOut * n)()
+        ob, keep2 = self._out_buffers(bufs, n)
+        rc = _lib.sb_decode_columns_async(self._h, ins, n, MEM_HOST if out == "host" else MEM_DEVICE, ob, outs)
+        if rc != _capi.SB_OK:
+            raise StrawboatError(rc, _lib.sb_last_error(self._h).decode())
+        ctx = self
+
+        class Handle:
+            def ready(self_):
+                return bool(_lib.sb_decode_ready(ctx._h))
+
+            def wait(self_, raise_on_page_error=True):
+                rc = _lib.sb_decode_wait(ctx._h)
+                self_._keep = (ins, keep, ob, keep2, columns)
+                if rc != _capi.SB_OK and (raise_on_page_error or not any(outs[i]._owner for i in range(n))):
+                    msg = _lib.sb_last_error(ctx._h).decode()
+                    _lib.sb_release_columns(ctx._h, outs, n)
+                    raise StrawboatError(rc, msg)
+                group = _OutGroup(ctx, outs, n, [len(c.metas) for c in columns])
+                res = [Decoded(ctx, columns[i].type, outs[i], i, group, columns[i].leaf.n_nested, copy) for i in range(n)]
+                if out == "host" and copy:
+                    group.release()
+                return res
+        return Handle()
+
+    def decode_columns_into(self, columns, bufs, out="device"):
+        """sb_decode_columns_into: decode straight into caller-owned buffers (see plan_columns)"""
+        return self.decode_columns_async(columns, out=out, bufs=bufs).wait()
 
     def batch_read_array(self, column, out="host"):
         """read::batch_read::batch_read_array for one leaf column."""

@@ -47,7 +47,7 @@ class Stats(C.Structure):
     _fields_ = [("pages", C.c_uint64), ("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("device_ms", C.c_float), ("codec_pages", C.c_uint64 * 32),
                 ("main_kernel_ms", C.c_float), ("lz4_kernel_ms", C.c_float),
-                ("lz4_bytes", C.c_uint64), ("host_ms", C.c_float)]
+                ("lz4_bytes", C.c_uint64), ("host_ms", C.c_float), ("light_kernel_ms", C.c_float)]
 
 
 class WriteOptions(C.Structure):
@@ -71,6 +71,15 @@ class PageInfo(C.Structure):
 class EncodedColumn(C.Structure):
     _fields_ = [("bytes", C.c_void_p), ("nbytes", C.c_uint64), ("metas", C.POINTER(PageMeta)),
                 ("n_pages", C.c_uint64), ("mem", C.c_int32), ("_owner", C.c_void_p)]
+
+
+class OutBuffers(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("values_cap", C.c_uint64), ("offsets", C.c_void_p), ("offsets_cap", C.c_uint64),
+                ("validity", C.c_void_p), ("validity_cap", C.c_uint64)]
+
+
+class ColumnSizes(C.Structure):
+    _fields_ = [("length", C.c_uint64), ("values_bytes", C.c_uint64), ("offsets_bytes", C.c_uint64), ("validity_bytes", C.c_uint64)]
 
 
 class GatherStats(C.Structure):
@@ -105,7 +114,8 @@ EXPORTS = ["sb_ctx_create", "sb_ctx_destroy", "sb_ctx_set_stream", "sb_last_erro
            "sb_decode_columns", "sb_decode_pages", "sb_release_columns", "sb_last_stats",
            "sb_encode_columns", "sb_release_encoded", "sb_stat_page",
            "sb_comm_unique_id", "sb_comm_create", "sb_comm_destroy", "sb_gather_encoded",
-           "sb_nested_levels", "sb_free_device", "sb_export_arrow"]
+           "sb_nested_levels", "sb_free_device", "sb_export_arrow",
+           "sb_plan_columns", "sb_decode_columns_into", "sb_decode_columns_async", "sb_decode_wait", "sb_decode_ready"]
 
 
 def load():
@@ -154,4 +164,13 @@ def load():
     L.sb_free_device.restype = None
     L.sb_export_arrow.argtypes = [C.c_void_p, C.POINTER(Field), C.POINTER(ColumnOut), C.c_uint64, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.sb_export_arrow.restype = C.c_int32
+    L.sb_plan_columns.argtypes = [C.c_void_p, C.POINTER(ColumnIn), C.c_uint64, C.POINTER(ColumnSizes)]
+    L.sb_plan_columns.restype = C.c_int32
+    for f in (L.sb_decode_columns_into, L.sb_decode_columns_async):
+        f.argtypes = [C.c_void_p, C.POINTER(ColumnIn), C.c_uint64, C.c_int32, C.POINTER(OutBuffers), C.POINTER(ColumnOut)]
+        f.restype = C.c_int32
+    L.sb_decode_wait.argtypes = [C.c_void_p]
+    L.sb_decode_wait.restype = C.c_int32
+    L.sb_decode_ready.argtypes = [C.c_void_p]
+    L.sb_decode_ready.restype = C.c_int32
     return L

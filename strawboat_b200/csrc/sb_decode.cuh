@@ -602,7 +602,10 @@ template <int W> __device__ bool dec_patas(Dctx &cx, const uint8_t *src, uint32_
 // (integer/mod.rs:72-117, double/mod.rs:69-114).  LEVEL bounds the codec nesting
 // (Dict -> indices, Freq -> exceptions; at most 3 stacked headers).
 // ------------------------------------------------------------------------------------
-template <int LEVEL>
+// LIGHT: the instantiation of the "light" decode kernel (sb_lib.cu): flat fixed-width pages whose codec tree only
+// holds None / OneValue / RLE / Bitpacking / DeltaBitpacking / Dict over those.  Everything serial or table heavy
+// (LZ4 / Snappy / Zstd blocks, Freq, Patas) is compiled out, which is what lets that kernel run at 8 CTAs per SM.
+template <int LEVEL, bool LIGHT = false>
 __device__ bool decode_fixed(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, int W, bool is_float,
                              uint8_t *dst, uint32_t *consumed);
 
@@ -625,20 +628,86 @@ template <int W> struct GenDict {
 };
 
 // Dict (integer/dict.rs:75-103): [VALUE_BLOCK<u32> indices][u32 k][k * W bytes]
-template <int LEVEL, int W>
+template <int LEVEL, int W, bool LIGHT>
 __device__ bool dec_dict(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, uint8_t *dst) {
+  using T = typename Elem<W>::T;
   if constexpr (LEVEL >= 2) {
     cx.flag(SB_OUT_OF_SPEC);
     return false;
   } else {
     Arena mark = cx.ar;
+    // ---- fused path: indices bit-packed at one width (what the chooser picks for 8192-row pages): every warp
+    //      unpacks a 128-index block and gathers straight from the table -- no index buffer, no second pass
+    if (avail >= 10 && src[0] == SB_C_BITPACK && (n & 127u) == 0 && n) {
+      const uint32_t compressed = ld_u32u(src + 1), nblk = n >> 7, bits0 = src[9], stride = 1 + 16 * bits0;
+      bool same = compressed <= avail - 9 && bits0 <= 32 && uint64_t(nblk) * stride <= compressed;
+      if (same)
+        for (uint32_t b = threadIdx.x; b < nblk; b += SB_NT) same &= src[9 + b * stride] == bits0;
+      if (__syncthreads_and(same)) {
+        const uint32_t used = 9 + compressed;
+        if (avail - used < 4) {
+          cx.flag(SB_IO);
+          return false;
+        }
+        const uint32_t k = ld_u32u(src + used);
+        const uint8_t *table = src + used + 4;
+        if (uint64_t(k) * W > uint64_t(avail - used - 4)) { // dict.rs:80-86
+          cx.flag(SB_OUT_OF_SPEC);
+          return false;
+        }
+        const uint8_t *tab = table;
+        bool aligned = (uintptr_t(table) & ((W > 16 ? 16 : W) - 1)) == 0;
+        if (!aligned) {
+          uint8_t *t2 = static_cast<uint8_t *>(cx.ar.alloc_shared(uint64_t(k) * W));
+          if (t2) {
+            copy_bytes(t2, table, uint64_t(k) * W);
+            tab = t2;
+            aligned = true;
+          }
+        }
+        __syncthreads();
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        T *out = reinterpret_cast<T *>(dst);
+        for (uint32_t b = warp; b < nblk; b += SB_NWARP) {
+          const uint4 v = bp_unpack_lane(src + 9 + b * stride + 1, bits0, lane);
+          const uint32_t ids[4] = {v.x, v.y, v.z, v.w};
+          T vals[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t id = ids[j];
+            if (id >= k) { // data[*i as usize] out of bounds panics (integer/dict.rs:100)
+              cx.flag(SB_PANIC);
+              id = 0;
+            }
+            vals[j] = (k == 0) ? T{} : (aligned ? reinterpret_cast<const T *>(tab)[id] : ld_elem_u<W>(tab + uint64_t(id) * W));
+          }
+          T *o = out + b * 128 + lane * 4;
+          if constexpr (W == 4) {
+            if ((uintptr_t(o) & 15) == 0) {
+              *reinterpret_cast<uint4 *>(o) = make_uint4(uint32_t(vals[0]), uint32_t(vals[1]), uint32_t(vals[2]), uint32_t(vals[3]));
+              continue;
+            }
+          } else if constexpr (W == 8) {
+            if ((uintptr_t(o) & 15) == 0) {
+              reinterpret_cast<uint4 *>(o)[0] = make_uint4(uint32_t(vals[0]), uint32_t(vals[0] >> 32), uint32_t(vals[1]), uint32_t(vals[1] >> 32));
+              reinterpret_cast<uint4 *>(o)[1] = make_uint4(uint32_t(vals[2]), uint32_t(vals[2] >> 32), uint32_t(vals[3]), uint32_t(vals[3] >> 32));
+              continue;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = vals[j];
+        }
+        cx.ar = mark;
+        return true;
+      }
+    }
     uint32_t *idx = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
     if (!idx) {
       cx.flag(SB_NYI);
       return false;
     }
     uint32_t used = 0;
-    if (!decode_fixed<LEVEL + 1>(cx, src, avail, n, 4, false, reinterpret_cast<uint8_t *>(idx), &used)) return false;
+    if (!decode_fixed<LEVEL + 1, LIGHT>(cx, src, avail, n, 4, false, reinterpret_cast<uint8_t *>(idx), &used)) return false;
     if (avail - used < 4) {
       cx.flag(SB_IO);
       return false;
@@ -782,18 +851,36 @@ __device__ bool dec_freq(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t 
   }
 }
 
-template <int LEVEL, int W>
+template <int LEVEL, int W, bool LIGHT>
 __device__ __forceinline__ bool decode_fixed_w(Dctx &cx, int codec, const uint8_t *body, uint32_t compressed,
                                                uint32_t body_avail, uint32_t n, bool is_float, uint8_t *dst) {
+  if constexpr (LIGHT) { // sb_classify_kernel only sends codec trees without these here; anything else is a logic error
+    if (codec == SB_C_LZ4 || codec == SB_C_ZSTD || codec == SB_C_SNAPPY || codec == SB_C_FREQ || codec == SB_C_PATAS) {
+      cx.flag(SB_PANIC);
+      return false;
+    }
+  }
   switch (codec) {
   case SB_C_NONE:
+    if constexpr (LIGHT) {
+      if (uint64_t(compressed) != uint64_t(n) * W) { // copy_from_slice length mismatch panics (basic.rs:68)
+        cx.flag(SB_PANIC);
+        return false;
+      }
+      stream_copy(cx, dst, body, uint64_t(n) * W);
+      return true;
+    }
   case SB_C_LZ4:
   case SB_C_ZSTD:
-  case SB_C_SNAPPY: return dec_basic(cx, codec, body, compressed, dst, uint64_t(n) * W);
+  case SB_C_SNAPPY:
+    if constexpr (!LIGHT) return dec_basic(cx, codec, body, compressed, dst, uint64_t(n) * W);
+    return false;
   case SB_C_RLE: return dec_rle<W>(cx, body, min(compressed, body_avail), n, dst);
   case SB_C_ONEVALUE: return dec_onevalue<W>(cx, body, body_avail, 0, n, dst);
-  case SB_C_DICT: return dec_dict<LEVEL, W>(cx, body, body_avail, n, dst);
-  case SB_C_FREQ: return dec_freq<LEVEL, W>(cx, body, body_avail, n, is_float, dst);
+  case SB_C_DICT: return dec_dict<LEVEL, W, LIGHT>(cx, body, body_avail, n, dst);
+  case SB_C_FREQ:
+    if constexpr (!LIGHT) return dec_freq<LEVEL, W>(cx, body, body_avail, n, is_float, dst);
+    return false;
   case SB_C_BITPACK:
   case SB_C_DELTABP:
     if (is_float) { // double/mod.rs:143-158
@@ -812,14 +899,14 @@ __device__ __forceinline__ bool decode_fixed_w(Dctx &cx, int codec, const uint8_
       cx.flag(SB_OUT_OF_SPEC);
       return false;
     }
-    if constexpr (W == 4 || W == 8) return dec_patas<W>(cx, body, body_avail, n, dst);
+    if constexpr (!LIGHT && (W == 4 || W == 8)) return dec_patas<W>(cx, body, body_avail, n, dst);
     cx.flag(SB_OUT_OF_SPEC);
     return false;
   default: cx.flag(SB_OUT_OF_SPEC); return false; // compression/mod.rs:78-80
   }
 }
 
-template <int LEVEL>
+template <int LEVEL, bool LIGHT>
 __device__ bool decode_fixed(Dctx &cx, const uint8_t *src, uint32_t avail, uint32_t n, int W, bool is_float,
                              uint8_t *dst, uint32_t *consumed) {
   if (avail < 9) { // read_compress_header (read_basic.rs:181-189)
@@ -836,12 +923,12 @@ __device__ bool decode_fixed(Dctx &cx, const uint8_t *src, uint32_t avail, uint3
   }
   *consumed = 9 + compressed;
   switch (W) {
-  case 1: return decode_fixed_w<LEVEL, 1>(cx, codec, body, compressed, body_avail, n, is_float, dst);
-  case 2: return decode_fixed_w<LEVEL, 2>(cx, codec, body, compressed, body_avail, n, is_float, dst);
-  case 4: return decode_fixed_w<LEVEL, 4>(cx, codec, body, compressed, body_avail, n, is_float, dst);
-  case 16: return decode_fixed_w<LEVEL, 16>(cx, codec, body, compressed, body_avail, n, is_float, dst);
-  case 32: return decode_fixed_w<LEVEL, 32>(cx, codec, body, compressed, body_avail, n, is_float, dst);
-  default: return decode_fixed_w<LEVEL, 8>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  case 1: return decode_fixed_w<LEVEL, 1, LIGHT>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  case 2: return decode_fixed_w<LEVEL, 2, LIGHT>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  case 4: return decode_fixed_w<LEVEL, 4, LIGHT>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  case 16: return decode_fixed_w<LEVEL, 16, LIGHT>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  case 32: return decode_fixed_w<LEVEL, 32, LIGHT>(cx, codec, body, compressed, body_avail, n, is_float, dst);
+  default: return decode_fixed_w<LEVEL, 8, LIGHT>(cx, codec, body, compressed, body_avail, n, is_float, dst);
   }
 }
 

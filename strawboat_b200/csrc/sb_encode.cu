@@ -344,6 +344,7 @@ int32_t sb_encode_columns(sb_ctx *ctx, const sb_leaf_array *cols, uint64_t n_col
   if (opts->default_compression != SB_C_NONE && opts->default_compression != SB_C_LZ4 && opts->default_compression != SB_C_SNAPPY &&
       opts->default_compression != SB_C_ZSTD)
     return fail(ctx, SB_OUT_OF_SPEC, "default_compression must be a common codec (None / LZ4 / Zstd / Snappy)");
+  if (ctx->pending.active) sb_decode_finish_pending(ctx); // the table buffers are shared with an in-flight decode call
   SB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   std::memset(outs, 0, sizeof(sb_encoded_column) * n_cols);

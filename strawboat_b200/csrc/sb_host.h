@@ -31,23 +31,39 @@ struct EncOwner { // what an sb_encoded_column owns (sb_encode_columns, sb_gathe
   void *metas = nullptr;
 };
 
+struct DecodePending { // a submitted decode call whose results have not been collected yet (sb_decode_wait)
+  bool active = false;
+  uint64_t n_cols = 0, n_pages_total = 0, n_items = 0;
+  int32_t out_mem = 0;
+  sb_column_out *outs = nullptr;
+  std::vector<Owner *> owners;
+  std::vector<uint64_t> col_pages;
+  size_t off_status = 0, off_counters = 0;
+  bool any_fixed = false;
+  uint64_t bytes_in = 0, bytes_out = 0;
+  double t_host0 = 0, t_planned = 0, t_submitted = 0;
+};
+
 struct sb_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, aux = nullptr;
+  cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr;
   bool own_stream = false;
   std::string err;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_cls = nullptr;
   cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr, ev_lz0 = nullptr, ev_lz1 = nullptr; // per-kernel timing
+  cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr, ev_join2 = nullptr;                 // light decode kernel (third stream)
   int sm_count = 0;
   int max_smem_optin = 0;
-  int lz4_occ = 0, occ_val = 0; // cached occupancy queries
+  int lz4_occ = 0, occ_val = 0, light_occ = 0; // cached occupancy queries
   uint32_t occ_smem = 0;
   DevBuf d_tables, d_scratch, d_entries;
   void *h_tables = nullptr;
   size_t h_tables_cap = 0;
   std::vector<PinnedBlock> pinned_free; // pinned host blocks are expensive to create: recycled
   sb_stats stats{};
+  DecodePending pending;
 };
+int32_t sb_decode_finish_pending(sb_ctx *ctx); // sb_lib.cu: collect an outstanding asynchronous decode (no-op when none)
 
 inline int fail(sb_ctx *ctx, int code, const std::string &msg) {
   if (ctx) ctx->err = msg;

@@ -25,6 +25,7 @@ namespace sb {
 
 __device__ __forceinline__ bool is_fixed_type(int t) { return (t >= SB_I8 && t <= SB_F64) || t == SB_I128 || t == SB_I256; }
 
+constexpr uint32_t kLightSmem = 26 * 1024;   // light kernel: 8 CTAs / SM
 constexpr uint32_t kSmemMax = 74 * 1024;     // dynamic shared memory per CTA: 3 CTAs / SM
 constexpr uint32_t kSmemMin = 40 * 1024;
 constexpr uint32_t kArenaMin = 6 * 1024;     // arena left after the largest staged page
@@ -100,14 +101,46 @@ __device__ __forceinline__ bool lz4_stored_block(const uint8_t *s, uint32_t clen
 
 __device__ __forceinline__ uint32_t ldg_u32u(const uint8_t *p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); }
 
+constexpr uint8_t SB_FLAG_HEAVY = 0x80; // side_flags bit: the page belongs to the full decode kernel
+// codec trees the light decode kernel handles (flat fixed-width page; `h` = hdr9 of the value block)
+__device__ __forceinline__ bool light_codec_tree(const uint8_t *h, uint32_t avail) {
+  if (avail < 9) return false;
+  const uint32_t c = h[0];
+  if (c == SB_C_NONE || c == SB_C_ONEVALUE || c == SB_C_RLE || c == SB_C_BITPACK || c == SB_C_DELTABP) return true;
+  if (c == SB_C_DICT && avail >= 18) { // the index sub-page
+    const uint32_t s = h[9];
+    return s == SB_C_NONE || s == SB_C_ONEVALUE || s == SB_C_RLE || s == SB_C_BITPACK;
+  }
+  return false;
+}
+
 __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, uint32_t n_pages,
-                                   Lz4Job *jobs, uint32_t *n_jobs, uint8_t *side_flags, const PageAux *__restrict__ aux) {
+                                   Lz4Job *jobs, uint32_t *n_jobs, uint8_t *side_flags, const PageAux *__restrict__ aux, uint32_t light_cap) {
   const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_pages) return;
   const PageDesc pg = pages[i];
   const ColDesc col = cols[pg.col];
-  if (!is_fixed_type(col.type)) return;
   const bool nested = col.n_nested > 1;
+  if (!is_fixed_type(col.type) || nested) {
+    if (lane == 0) side_flags[i] = SB_FLAG_HEAVY; // binary, boolean, nested: the full kernel
+    if (!is_fixed_type(col.type)) return;
+  }
+  // flat fixed-width page: family by codec tree and staging size (pages the light kernel cannot stage stay heavy)
+  uint8_t fam = 0;
+  if (!nested) {
+    uint32_t vb0 = 0;
+    bool hdr_ok = true;
+    if (col.nullable) {
+      hdr_ok = pg.len >= 4;
+      const uint32_t L = hdr_ok ? ldg_u32u(pg.src) : 0;
+      hdr_ok = hdr_ok && L <= pg.len - 4;
+      vb0 = 4 + L;
+    }
+    const bool small = pg.len + 32 <= light_cap;
+    fam = (hdr_ok && small && light_codec_tree(pg.src + vb0, pg.len - vb0)) ? 0 : SB_FLAG_HEAVY;
+  } else {
+    fam = SB_FLAG_HEAVY;
+  }
   uint32_t vb, clen;
   uint64_t n_vals = pg.num_values;
   const uint8_t *body = pg.src;
@@ -121,15 +154,25 @@ __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const Col
     body_len -= uint32_t(lv);
     n_vals = aux[pg.aux].cnt[col.n_nested - 1];
   } else if (plain_page(pg.src, pg.len, col.nullable != 0, uint64_t(pg.num_values) * uint32_t(col.W))) {
-    if (lane == 0) side_flags[i] = 3;
+    // plain pages stream through the TMA ring whatever their size: light unless the validity section needs a large stage
+    const uint32_t stage = pg.len - pg.num_values * uint32_t(col.W);
+    if (lane == 0) side_flags[i] = 3 | ((!col.nullable || stage + 32 <= light_cap) ? 0 : SB_FLAG_HEAVY);
     return;
   }
-  if (!lz4_side_page(body, body_len, !nested && col.nullable != 0, &vb, &clen)) return;
+  if (!lz4_side_page(body, body_len, !nested && col.nullable != 0, &vb, &clen)) {
+    if (lane == 0) side_flags[i] = fam;
+    return;
+  }
   const uint64_t dlen64 = n_vals * uint32_t(col.W);
-  if (dlen64 > SB_LZ4_MAXPOS / 2 || clen > SB_LZ4_MAXPOS / 2) return; // positions are 30-bit in sb_lz4_kernel
+  if (dlen64 > SB_LZ4_MAXPOS / 2 || clen > SB_LZ4_MAXPOS / 2) { // positions are 30-bit in sb_lz4_kernel: decoded in the full kernel
+    if (lane == 0) side_flags[i] = SB_FLAG_HEAVY;
+    return;
+  }
   const uint32_t dlen = uint32_t(dlen64);
+  // an LZ4 page leaves the validity section (if any) to the decode kernel: light when that stages small
+  const uint8_t lz_fam = nested ? SB_FLAG_HEAVY : ((!col.nullable || vb + 32 <= light_cap) ? 0 : SB_FLAG_HEAVY);
   if (lz4_stored_block(body + vb + 9, clen, dlen)) {
-    if (lane == 0) side_flags[i] = 2;
+    if (lane == 0) side_flags[i] = 2 | (nested || pg.len + 32 > light_cap ? SB_FLAG_HEAVY : lz_fam);
     return;
   }
   if (lane != 0) return;
@@ -144,7 +187,7 @@ __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const Col
   const bool big = clen >= 8192;
   uint32_t slot = big ? atomicAdd(n_jobs, 1u) : n_pages - 1 - atomicAdd(n_jobs + 1, 1u);
   jobs[slot] = j;
-  side_flags[i] = 1;
+  side_flags[i] = 1 | lz_fam;
 }
 
 // One CTA = SB_LZ4_PAIRS scanner warps (warps 0..PAIRS-1, one warpgroup) + as many mover warps (the next
@@ -221,11 +264,18 @@ __global__ void __launch_bounds__(SB_LZ4_CTA, 3)
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ bool is_binary_type(int t) { return t == SB_BINARY || t == SB_LARGE_BINARY; }
 
-__global__ void __launch_bounds__(SB_NT, 4)
-    sb_decode_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols,
+// Two instantiations share this body.  LIGHT = flat fixed-width pages whose codec tree is None / OneValue / RLE /
+// Bitpacking / DeltaBitpacking / Dict over those (sb_classify_kernel sets SB_FLAG_HEAVY on everything else): no LZ4
+// scanner / mover, no Freq, Patas, binary, boolean or nested code, so it compiles to half the registers and runs at
+// 8 CTAs per SM -- the dependent chain of a small page (ticket -> descriptors -> TMA -> header -> gather -> store)
+// is hidden by twice as many pages in flight.  Both kernels walk the same item list; each takes the items of its
+// family (thread 0 skips the others while drawing tickets).
+template <bool LIGHT>
+__device__ __forceinline__ void decode_body(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols,
                      const WorkItem *__restrict__ items, uint32_t n_items, uint32_t *counter, uint8_t *scratch,
                      uint64_t scratch_per_cta, int32_t *status, uint32_t stage_cap, uint32_t smem_bytes,
-                     const uint8_t *__restrict__ side_flags, PageAux *aux, BinEntry *entries, uint32_t *codec_hist, int pass) {
+                     const uint8_t *__restrict__ side_flags, PageAux *aux, BinEntry *entries, uint32_t *codec_hist, int pass,
+                     bool split) {
   extern __shared__ __align__(128) uint8_t dsm[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ __align__(8) uint64_t s_rbar[SB_RING_STAGES];
@@ -235,11 +285,20 @@ __global__ void __launch_bounds__(SB_NT, 4)
   __shared__ uint32_t s_item;
 
   const uint32_t tid = threadIdx.x;
+  // next item of this kernel's family (thread 0)
+  auto draw = [&]() -> uint32_t {
+    for (;;) {
+      const uint32_t t = atomicAdd(counter, 1u);
+      if (t >= n_items || !split) return t;
+      const bool heavy = (side_flags[items[t].page] & SB_FLAG_HEAVY) != 0;
+      if (heavy != LIGHT) return t;
+    }
+  };
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     for (int i = 0; i < SB_RING_STAGES; ++i) mbar_init(&s_rbar[i], 1);
     fence_mbar_init();
-    s_item = atomicAdd(counter, 1u);
+    s_item = draw();
     s_err = 0;
   }
   __syncthreads();
@@ -250,11 +309,11 @@ __global__ void __launch_bounds__(SB_NT, 4)
     if (it >= n_items) break;
     // the next item's ticket is drawn now and travels under this item's work
     uint32_t next_it = 0;
-    if (tid == 0) next_it = atomicAdd(counter, 1u);
+    if (tid == 0) next_it = draw();
     const WorkItem wi = items[it];
     const PageDesc pg = pages[wi.page];
     const ColDesc &col = cols[pg.col];
-    const uint32_t side = (pass == 1 && side_flags != nullptr) ? side_flags[wi.page] : 0u;
+    const uint32_t side = (pass == 1 && side_flags != nullptr) ? (side_flags[wi.page] & 3u) : 0u;
     const bool lz4_side = side == 1; // value block decoded by sb_lz4_kernel
     const bool stored = side == 2;   // LZ4 block that is one literal run: plain copy here
     if (lz4_side && !col.nullable && col.n_nested <= 1) { // value block handled by sb_lz4_kernel, nothing else in the page
@@ -305,7 +364,7 @@ __global__ void __launch_bounds__(SB_NT, 4)
     const uint32_t avail = pg.len;
     uint32_t n = pg.num_values;
     bool ok = true;
-    const bool nested = col.n_nested > 1;
+    const bool nested = !LIGHT && col.n_nested > 1;
     const bool flat_fixed = is_fixed_type(col.type) && !nested;
 
     if (col.type == SB_NULL) {
@@ -339,9 +398,9 @@ __global__ void __launch_bounds__(SB_NT, 4)
         }
       } else if (wi.tile == 0) {
         uint32_t used = 0;
-        if (!lz4_side) ok = decode_fixed<0>(cx, p, avail, n, col.W, col.is_float != 0, dst, &used);
+        if (!lz4_side) ok = decode_fixed<0, LIGHT>(cx, p, avail, n, col.W, col.is_float != 0, dst, &used);
       }
-    } else if (pass == 1 && !staged && wi.tile != 0xffffffffu && wi.tile != 0 && is_binary_type(col.type) && !nested) {
+    } else if (!LIGHT && pass == 1 && !staged && wi.tile != 0xffffffffu && wi.tile != 0 && is_binary_type(col.type) && !nested) {
       // ---- oversized binary page, tiles 1..: a slice of the plain value bytes found by the plan pass
       const PageAux &ax = aux[pg.aux];
       const uint64_t lo = uint64_t(wi.tile - 1) * kBinTile;
@@ -352,11 +411,13 @@ __global__ void __launch_bounds__(SB_NT, 4)
       uint32_t vb = 0;
       uint64_t out_elem = pg.out_elem;
       if (nested) {
-        // levels section: NestedState entries + leaf validity; n becomes the leaf slot count
-        uint32_t leaf_len = 0;
-        vb = decode_levels(cx, p, avail, n, col, pass, ax, pg.last != 0, &leaf_len);
-        if (vb == 0xffffffffu) ok = false;
-        n = leaf_len;
+        if constexpr (!LIGHT) {
+          // levels section: NestedState entries + leaf validity; n becomes the leaf slot count
+          uint32_t leaf_len = 0;
+          vb = decode_levels(cx, p, avail, n, col, pass, ax, pg.last != 0, &leaf_len);
+          if (vb == 0xffffffffu) ok = false;
+          n = leaf_len;
+        }
       } else if (col.nullable) {
         if (pass == 1) {
           vb = decode_validity(cx, p, avail, n, col.validity, pg.out_elem);
@@ -371,25 +432,27 @@ __global__ void __launch_bounds__(SB_NT, 4)
       // plain value bytes of an oversized flat binary page travel as tiles 1.. (same predicate as the host's item list)
       const bool vtiled = pass == 1 && !staged && wi.tile == 0 && is_binary_type(col.type) && !nested && ax && ax->val_pos != 0;
       if (ok && pass == 0) {
-        if (is_binary_type(col.type)) {
-          uint64_t vbytes = 0;
-          uint32_t val_pos = 0, n_ent = 0;
-          ok = binary_page_size(cx, p, avail, vb, n, entries + pg.tab_off, &vbytes, &val_pos, &n_ent);
-          ok = !__syncthreads_or(!ok || *cx.err != 0); // per-thread flags (bad dictionary index, ...) count too
-          if (tid == 0) {
-            ax->value_bytes = ok ? vbytes : 0;
-            ax->val_pos = ok ? val_pos : 0;
-            ax->n_ent = ok ? n_ent : 0;
-            ax->failed = ok ? 0u : 1u;
+        if constexpr (!LIGHT) {
+          if (is_binary_type(col.type)) {
+            uint64_t vbytes = 0;
+            uint32_t val_pos = 0, n_ent = 0;
+            ok = binary_page_size(cx, p, avail, vb, n, entries + pg.tab_off, &vbytes, &val_pos, &n_ent);
+            ok = !__syncthreads_or(!ok || *cx.err != 0); // per-thread flags (bad dictionary index, ...) count too
+            if (tid == 0) {
+              ax->value_bytes = ok ? vbytes : 0;
+              ax->val_pos = ok ? val_pos : 0;
+              ax->n_ent = ok ? n_ent : 0;
+              ax->failed = ok ? 0u : 1u;
+            }
+          } else if (tid == 0) {
+            ax->value_bytes = 0;
           }
-        } else if (tid == 0) {
-          ax->value_bytes = 0;
         }
       } else if (ok && pass == 1 && ax && ax->failed) {
         // rejected by the plan pass (status already holds the reason): its outputs were never sized
       } else if (ok) {
-        if (col.type == SB_BOOL) {
-          ok = decode_boolean(cx, p + vb, avail - vb, n, col.values, out_elem);
+        if (!LIGHT && col.type == SB_BOOL) {
+          if constexpr (!LIGHT) ok = decode_boolean(cx, p + vb, avail - vb, n, col.values, out_elem);
         } else if (is_fixed_type(col.type)) {
           uint32_t used = 0;
           // top-level LZ4 blocks are decoded by sb_lz4_kernel (same predicate as sb_classify_kernel)
@@ -399,18 +462,20 @@ __global__ void __launch_bounds__(SB_NT, 4)
           } else if (plain) { // value bytes stream from global memory behind the staged validity section
             stream_copy(cx, col.values + out_elem * uint64_t(col.W), pg.src + vb + 9, uint64_t(n) * uint32_t(col.W));
           } else if (!lz4_side)
-            ok = decode_fixed<0>(cx, p + vb, avail - vb, n, col.W, col.is_float != 0,
-                                 col.values + out_elem * uint64_t(col.W), &used);
-        } else if (col.type == SB_BINARY) {
-          ok = decode_binary<4>(cx, p, avail, vb, n, reinterpret_cast<int32_t *>(col.offsets) + out_elem,
-                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off, vtiled,
-                                ax->n_ent, ax->value_bytes);
-        } else if (col.type == SB_LARGE_BINARY) {
-          ok = decode_binary<8>(cx, p, avail, vb, n, reinterpret_cast<int64_t *>(col.offsets) + out_elem,
-                                col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off, vtiled,
-                                ax->n_ent, ax->value_bytes);
+            ok = decode_fixed<0, LIGHT>(cx, p + vb, avail - vb, n, col.W, col.is_float != 0,
+                                        col.values + out_elem * uint64_t(col.W), &used);
+        } else if (!LIGHT && col.type == SB_BINARY) {
+          if constexpr (!LIGHT)
+            ok = decode_binary<4>(cx, p, avail, vb, n, reinterpret_cast<int32_t *>(col.offsets) + out_elem,
+                                  col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off, vtiled,
+                                  ax->n_ent, ax->value_bytes);
+        } else if (!LIGHT && col.type == SB_LARGE_BINARY) {
+          if constexpr (!LIGHT)
+            ok = decode_binary<8>(cx, p, avail, vb, n, reinterpret_cast<int64_t *>(col.offsets) + out_elem,
+                                  col.values + pg.out_byte, pg.out_byte, pg.ordinal == 0, entries + pg.tab_off, vtiled,
+                                  ax->n_ent, ax->value_bytes);
         } else {
-          cx.flag(SB_NYI);
+          cx.flag(LIGHT ? SB_PANIC : SB_NYI);
         }
       }
     }
@@ -424,6 +489,21 @@ __global__ void __launch_bounds__(SB_NT, 4)
     }
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(SB_NT, 4)
+    sb_decode_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, const WorkItem *__restrict__ items, uint32_t n_items,
+                     uint32_t *counter, uint8_t *scratch, uint64_t scratch_per_cta, int32_t *status, uint32_t stage_cap, uint32_t smem_bytes,
+                     const uint8_t *__restrict__ side_flags, PageAux *aux, BinEntry *entries, uint32_t *codec_hist, int pass, int split) {
+  decode_body<false>(pages, cols, items, n_items, counter, scratch, scratch_per_cta, status, stage_cap, smem_bytes, side_flags, aux, entries,
+                     codec_hist, pass, split != 0);
+}
+__global__ void __launch_bounds__(SB_NT, 8)
+    sb_decode_light_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, const WorkItem *__restrict__ items,
+                           uint32_t n_items, uint32_t *counter, uint8_t *scratch, uint64_t scratch_per_cta, int32_t *status, uint32_t stage_cap,
+                           uint32_t smem_bytes, const uint8_t *__restrict__ side_flags, uint32_t *codec_hist) {
+  decode_body<true>(pages, cols, items, n_items, counter, scratch, scratch_per_cta, status, stage_cap, smem_bytes, side_flags, nullptr, nullptr,
+                    codec_hist, 1, true);
 }
 
 } // namespace sb
@@ -471,6 +551,9 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out) {
     return SB_CUDA;
   }
   ctx->own_stream = true;
+  cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
+  for (cudaEvent_t *ev : {&ctx->ev_l0, &ctx->ev_l1}) cudaEventCreate(ev);
+  cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming);
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
   for (cudaEvent_t *ev : {&ctx->ev_m0, &ctx->ev_m1, &ctx->ev_lz0, &ctx->ev_lz1}) cudaEventCreate(ev);
@@ -494,9 +577,13 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out) {
 
 void sb_ctx_destroy(sb_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->pending.active) { // never collected: give its buffers back
+    sb_decode_finish_pending(ctx);
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->aux);
+  cudaStreamSynchronize(ctx->aux2);
   for (DevBuf *b : {&ctx->d_tables, &ctx->d_scratch, &ctx->d_entries})
     if (b->p) cudaFreeAsync(b->p, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
@@ -504,8 +591,11 @@ void sb_ctx_destroy(sb_ctx *ctx) {
   for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
   for (cudaEvent_t ev : {ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->ev_join, ctx->ev_cls, ctx->ev_m0, ctx->ev_m1, ctx->ev_lz0, ctx->ev_lz1})
     if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : {ctx->ev_l0, ctx->ev_l1, ctx->ev_join2})
+    if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->aux);
+  cudaStreamDestroy(ctx->aux2);
   delete ctx;
 }
 
@@ -656,14 +746,28 @@ static uint64_t bin_value_tiles(const sb_page_meta &m, uint64_t OW) {
   return (vmax + kBinTile - 1) / kBinTile;
 }
 
-int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, int32_t out_mem, sb_column_out *outs) {
+} // extern "C"
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Submits every copy and kernel of one decode call on the context's streams and records what sb_decode_finish_pending
+// needs to hand the results over.  `bufs` (optional): caller-owned output buffers per column.  `sizes` (optional):
+// plan only -- run the size pass, report the buffer sizes, decode nothing.
+static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, int32_t out_mem, sb_column_out *outs,
+                             const sb_out_buffers *bufs, sb_column_sizes *sizes) {
   if (!ctx) return SB_CUDA;
-  if (!cols || !outs || (out_mem != SB_MEM_HOST && out_mem != SB_MEM_DEVICE)) return fail(ctx, SB_INVALID_ARG, "bad arguments");
+  if (!cols || (!outs && !sizes) || (out_mem != SB_MEM_HOST && out_mem != SB_MEM_DEVICE)) return fail(ctx, SB_INVALID_ARG, "bad arguments");
+  if (ctx->pending.active) sb_decode_finish_pending(ctx); // one outstanding call per context: the previous one is collected first
+  std::vector<sb_column_out> plan_outs;
+  if (sizes) { // plan only: outputs are never materialised for the caller
+    plan_outs.resize(n_cols);
+    outs = plan_outs.data();
+  }
   SB_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   std::memset(outs, 0, sizeof(sb_column_out) * n_cols);
   ctx->stats = sb_stats{};
-  const auto t_host0 = std::chrono::steady_clock::now();
+  const double t_host0 = now_ms();
 
   // ---- host pass: validate, count pages / work items
   uint64_t n_pages_total = 0, n_items = 0, n_plan = 0, n_entries = 0, max_elems_bytes = 0;
@@ -711,6 +815,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   auto cleanup = [&]() {
     // kernels already launched on either stream may still write into the outputs: join before freeing
     cudaStreamSynchronize(ctx->aux);
+    cudaStreamSynchronize(ctx->aux2);
     cudaStreamSynchronize(st);
     for (void *d : d_inputs) cudaFreeAsync(d, st);
     d_inputs.clear();
@@ -763,7 +868,19 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   std::memset(h_aux, 0, sizeof(PageAux) * n_plan);
 
   // device allocation of an output buffer, owned by the column
-  auto dev_out = [&](Owner *ow, uint64_t bytes, bool zero, uint8_t **out) -> int {
+  // `user` / `cap`: a caller-owned DEVICE buffer for this output (sb_out_buffers, out_mem = SB_MEM_DEVICE): used in place
+  auto dev_out = [&](Owner *ow, uint64_t bytes, bool zero, uint8_t **out, void *user = nullptr, uint64_t cap = 0) -> int {
+    if (sizes) { // plan only: nothing is written, a token buffer keeps the bookkeeping uniform
+      bytes = 0;
+      user = nullptr;
+    }
+    if (user && out_mem == SB_MEM_DEVICE) {
+      if (cap < bytes) return fail(ctx, SB_INVALID_ARG, "caller-provided output buffer is too small (see sb_plan_columns)");
+      if (uintptr_t(user) & 15) return fail(ctx, SB_INVALID_ARG, "caller-provided output buffers must be 16-byte aligned");
+      if (zero && bytes) SB_CUDA_CHECK(ctx, cudaMemsetAsync(user, 0, std::min<uint64_t>(cap, align_up(bytes, 4)), st));
+      *out = static_cast<uint8_t *>(user);
+      return SB_OK;
+    }
     void *d = nullptr;
     SB_CUDA_CHECK(ctx, cudaMallocAsync(&d, bytes + 16, st));
     ow->dev.push_back(d);
@@ -771,6 +888,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     *out = static_cast<uint8_t *>(d);
     return SB_OK;
   };
+  auto ubuf = [&](uint64_t c) -> const sb_out_buffers * { return bufs ? &bufs[c] : nullptr; };
 
   uint64_t pi = 0, ii = 0, i0 = 0, ent = 0, bytes_in = 0, bytes_out = 0;
   bool any_fixed = false;
@@ -820,20 +938,21 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       o.length = rows;
       cd.length = rows;
       uint64_t bitmap_bytes = align_up((rows + 7) / 8, 4);
+      const sb_out_buffers *ub = ubuf(c);
       if (ci.leaf.type == SB_BOOL) {
         o.values_bytes = (rows + 7) / 8;
-        SB_TRY(dev_out(ow, bitmap_bytes, true, &cd.values));
+        SB_TRY(dev_out(ow, bitmap_bytes, true, &cd.values, ub ? ub->values : nullptr, ub ? ub->values_cap : 0));
       } else if (binary) {
         o.offsets_bytes = (rows + 1) * uint64_t(W);
-        SB_TRY(dev_out(ow, o.offsets_bytes, false, &cd.offsets));
-        SB_TRY_CUDA(cudaMemsetAsync(cd.offsets, 0, size_t(W), st)); // offsets[0] = 0 even for a column without pages
+        SB_TRY(dev_out(ow, o.offsets_bytes, false, &cd.offsets, ub ? ub->offsets : nullptr, ub ? ub->offsets_cap : 0));
+        if (!sizes) SB_TRY_CUDA(cudaMemsetAsync(cd.offsets, 0, size_t(W), st)); // offsets[0] = 0 even for a column without pages
       } else if (W && ci.leaf.type != SB_NULL) {
         o.values_bytes = rows * uint64_t(W);
-        SB_TRY(dev_out(ow, o.values_bytes, false, &cd.values));
+        SB_TRY(dev_out(ow, o.values_bytes, false, &cd.values, ub ? ub->values : nullptr, ub ? ub->values_cap : 0));
       }
       if (cd.nullable) {
         o.validity_bytes = (rows + 7) / 8;
-        SB_TRY(dev_out(ow, bitmap_bytes, true, &cd.validity));
+        SB_TRY(dev_out(ow, bitmap_bytes, true, &cd.validity, ub ? ub->validity : nullptr, ub ? ub->validity_cap : 0));
       }
     }
     // pages
@@ -898,10 +1017,19 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   Lz4Job *d_jobs = reinterpret_cast<Lz4Job *>(dT + off_jobs);
   PageAux *d_aux = reinterpret_cast<PageAux *>(dT + off_aux);
   BinEntry *d_entries = static_cast<BinEntry *>(ctx->d_entries.p);
-  static const bool dbg_timing = std::getenv("SB_TIMING") != nullptr; // diagnostic: host phases of the call on stderr
   const auto t_planned = std::chrono::steady_clock::now();
+  uint32_t grid_light = 0;
+  if (any_fixed && n_items) {
+    if (ctx->light_occ == 0) {
+      int q = 1;
+      SB_TRY_CUDA(cudaFuncSetAttribute(sb_decode_light_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, sb_decode_light_kernel, SB_NT, kLightSmem));
+      ctx->light_occ = std::max(1, q);
+    }
+    grid_light = uint32_t(std::min<uint64_t>(n_items, uint64_t(ctx->sm_count) * ctx->light_occ));
+  }
   if (n_items) {
-    SB_TRY(dev_reserve(ctx, ctx->d_scratch, scratch_per_cta * grid));
+    SB_TRY(dev_reserve(ctx, ctx->d_scratch, scratch_per_cta * (uint64_t(grid) + grid_light)));
     SB_TRY_CUDA(cudaMemcpyAsync(dT, hT, tables_bytes, cudaMemcpyHostToDevice, st));
     SB_TRY_CUDA(cudaMemsetAsync(dT + off_status, 0, zero_end - off_status, st));
     SB_TRY_CUDA(cudaEventRecord(ctx->ev0, st));
@@ -912,7 +1040,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     uint32_t grid0 = uint32_t(std::min<uint64_t>(n_plan, uint64_t(ctx->sm_count) * occ));
     sb_decode_kernel<<<grid0, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items0), uint32_t(n_plan),
                                                  d_counters + 4, static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta, d_status,
-                                                 stage_cap, smem, nullptr, d_aux, d_entries, d_counters + 5, 0);
+                                                 stage_cap, smem, nullptr, d_aux, d_entries, d_counters + 5, 0, 0);
     SB_TRY_CUDA(cudaGetLastError());
     ctx->stats.kernel_launches += 1;
     SB_TRY_CUDA(cudaMemcpyAsync(h_aux, d_aux, sizeof(PageAux) * n_plan, cudaMemcpyDeviceToHost, st));
@@ -955,7 +1083,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
         } else if (binary) {
           o.offsets_bytes = (rows + 1) * uint64_t(W);
           SB_TRY(dev_out(ow, o.offsets_bytes, false, &cd.offsets));
-          SB_TRY_CUDA(cudaMemsetAsync(cd.offsets, 0, size_t(W), st));
+          if (!sizes) SB_TRY_CUDA(cudaMemsetAsync(cd.offsets, 0, size_t(W), st));
         } else {
           o.values_bytes = rows * uint64_t(W);
           SB_TRY(dev_out(ow, o.values_bytes, false, &cd.values));
@@ -980,10 +1108,21 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
           return fail(ctx, SB_OUT_OF_SPEC, "column " + std::to_string(c) + ": more than 2 GiB of value bytes do not fit i32 offsets");
         }
         o.values_bytes = vbytes;
-        SB_TRY(dev_out(ow, vbytes, false, &cd.values));
+        const sb_out_buffers *ub = nested ? nullptr : ubuf(c);
+        SB_TRY(dev_out(ow, vbytes, false, &cd.values, ub ? ub->values : nullptr, ub ? ub->values_cap : 0));
       }
     }
     SB_TRY_CUDA(cudaMemcpyAsync(dT, hT, tables_bytes, cudaMemcpyHostToDevice, st));
+  }
+  if (sizes) { // sb_plan_columns: the sizes are known now; nothing else runs
+    for (uint64_t c = 0; c < n_cols; ++c) {
+      sizes[c].length = outs[c].length;
+      sizes[c].values_bytes = outs[c].values_bytes;
+      sizes[c].offsets_bytes = outs[c].offsets_bytes;
+      sizes[c].validity_bytes = outs[c].validity_bytes;
+    }
+    cleanup();
+    return SB_OK;
   }
 
   // ---- pass 1 (decode)
@@ -997,7 +1136,7 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_fork, st));
       SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
       sb_classify_kernel<<<uint32_t((n_pages_total + 7) / 8), 256, 0, ctx->aux>>>(d_pages, d_cols, uint32_t(n_pages_total), d_jobs,
-                                                                                    d_counters + 2, d_flags, d_aux);
+                                                                                    d_counters + 2, d_flags, d_aux, kLightSmem - kArenaMin);
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_cls, ctx->aux));
       if (ctx->lz4_occ == 0) {
         int q = 1;
@@ -1014,15 +1153,31 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
       ctx->stats.kernel_launches += 2;
     }
-    if (any_fixed) SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_cls, 0));
+    if (any_fixed) {
+      // the light kernel (flat fixed-width pages with light codec trees) on its own stream, next to the full one
+      SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux2, ctx->ev_cls, 0));
+      SB_TRY_CUDA(cudaEventRecord(ctx->ev_l0, ctx->aux2));
+      sb_decode_light_kernel<<<grid_light, SB_NT, kLightSmem, ctx->aux2>>>(
+          d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items), uint32_t(n_items), d_counters + 37,
+          static_cast<uint8_t *>(ctx->d_scratch.p) + scratch_per_cta * grid, scratch_per_cta, d_status, kLightSmem - kArenaMin, kLightSmem, d_flags,
+          d_counters + 5);
+      SB_TRY_CUDA(cudaGetLastError());
+      SB_TRY_CUDA(cudaEventRecord(ctx->ev_l1, ctx->aux2));
+      SB_TRY_CUDA(cudaEventRecord(ctx->ev_join2, ctx->aux2));
+      ctx->stats.kernel_launches += 1;
+      SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_cls, 0));
+    }
     SB_TRY_CUDA(cudaEventRecord(ctx->ev_m0, st));
     sb_decode_kernel<<<grid, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items),
                                                 uint32_t(n_items), d_counters, static_cast<uint8_t *>(ctx->d_scratch.p),
                                                 scratch_per_cta, d_status, stage_cap, smem, any_fixed ? d_flags : nullptr, d_aux,
-                                                d_entries, d_counters + 5, 1);
+                                                d_entries, d_counters + 5, 1, any_fixed ? 1 : 0);
     SB_TRY_CUDA(cudaGetLastError());
     SB_TRY_CUDA(cudaEventRecord(ctx->ev_m1, st));
-    if (any_fixed) SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (any_fixed) {
+      SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+      SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+    }
     SB_TRY_CUDA(cudaEventRecord(ctx->ev1, st));
     ctx->stats.kernel_launches += 1;
     // statuses + codec histogram back (pinned), reuse the tail of the host table buffer
@@ -1030,10 +1185,16 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
   }
 
   // ---- results to the caller
-  auto to_caller = [&](Owner *ow, const void *dev, uint64_t bytes, void **out) -> int {
+  auto to_caller = [&](Owner *ow, const void *dev, uint64_t bytes, void **out, void *user = nullptr, uint64_t cap = 0) -> int {
     if (!dev) return SB_OK;
     if (out_mem == SB_MEM_DEVICE) {
       *out = const_cast<void *>(dev);
+      return SB_OK;
+    }
+    if (user) { // caller-owned host buffer (pinned memory keeps the copy asynchronous)
+      if (cap < bytes) return fail(ctx, SB_INVALID_ARG, "caller-provided output buffer is too small (see sb_plan_columns)");
+      if (bytes) SB_CUDA_CHECK(ctx, cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, st));
+      *out = user;
       return SB_OK;
     }
     PinnedBlock b;
@@ -1048,9 +1209,10 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
     sb_column_out &o = outs[c];
     Owner *ow = owners[c];
     const ColDesc &cd = h_cols[c];
-    SB_TRY(to_caller(ow, cd.values, o.values_bytes, &o.values));
-    SB_TRY(to_caller(ow, cd.offsets, o.offsets_bytes, &o.offsets));
-    SB_TRY(to_caller(ow, cd.validity, o.validity_bytes, reinterpret_cast<void **>(&o.validity)));
+    const sb_out_buffers *ub = cd.n_nested > 1 ? nullptr : ubuf(c);
+    SB_TRY(to_caller(ow, cd.values, o.values_bytes, &o.values, ub ? ub->values : nullptr, ub ? ub->values_cap : 0));
+    SB_TRY(to_caller(ow, cd.offsets, o.offsets_bytes, &o.offsets, ub ? ub->offsets : nullptr, ub ? ub->offsets_cap : 0));
+    SB_TRY(to_caller(ow, cd.validity, o.validity_bytes, reinterpret_cast<void **>(&o.validity), ub ? ub->validity : nullptr, ub ? ub->validity_cap : 0));
     for (int d = 0; d + 1 < cd.n_nested; ++d) {
       SB_TRY(to_caller(ow, cd.nest_off[d], (o.nested_len[d] + 1) * 8, reinterpret_cast<void **>(&o.nested_offsets[d])));
       SB_TRY(to_caller(ow, cd.nest_val[d], (o.nested_len[d] + 7) / 8, reinterpret_cast<void **>(&o.nested_validity[d])));
@@ -1060,37 +1222,74 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       bytes_out += (cd.nest_off[d] ? (o.nested_len[d] + 1) * 8 : 0) + (cd.nest_val[d] ? (o.nested_len[d] + 7) / 8 : 0);
   }
   for (void *d : d_inputs) cudaFreeAsync(d, st);
-  const auto t_submitted = std::chrono::steady_clock::now();
-  SB_TRY_CUDA(cudaStreamSynchronize(st));
-  const auto t_synced = std::chrono::steady_clock::now();
-  if (out_mem == SB_MEM_HOST) { // device copies no longer needed
+  // ---- everything is submitted: remember what the collection step needs
+  DecodePending &pd = ctx->pending;
+  pd.active = true;
+  pd.n_cols = n_cols;
+  pd.n_pages_total = n_pages_total;
+  pd.n_items = n_items;
+  pd.out_mem = out_mem;
+  pd.outs = outs;
+  pd.owners = owners;
+  pd.col_pages.resize(n_cols);
+  for (uint64_t c = 0; c < n_cols; ++c) pd.col_pages[c] = cols[c].n_pages;
+  pd.off_status = off_status;
+  pd.off_counters = off_counters;
+  pd.any_fixed = any_fixed;
+  pd.bytes_in = bytes_in;
+  pd.bytes_out = bytes_out;
+  pd.t_host0 = t_host0;
+  pd.t_planned = std::chrono::duration<double, std::milli>(t_planned.time_since_epoch()).count();
+  pd.t_submitted = now_ms();
+  return SB_OK;
+#undef SB_TRY
+#undef SB_TRY_CUDA
+}
+
+// Waits for a submitted decode call and hands its results over: per-page statuses, statistics, ownership.
+int32_t sb_decode_finish_pending(sb_ctx *ctx) {
+  DecodePending &pd = ctx->pending;
+  if (!pd.active) return SB_OK;
+  pd.active = false;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  sb_column_out *outs = pd.outs;
+  const uint64_t n_cols = pd.n_cols;
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    for (uint64_t c = 0; c < n_cols; ++c) outs[c]._owner = pd.owners[c];
+    sb_release_columns(ctx, outs, n_cols);
+    return fail(ctx, SB_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+  }
+  const double t_synced = now_ms();
+  if (pd.out_mem == SB_MEM_HOST) { // device copies no longer needed
     for (uint64_t c = 0; c < n_cols; ++c) {
-      for (void *p : owners[c]->dev) cudaFreeAsync(p, st);
-      owners[c]->dev.clear();
+      for (void *p : pd.owners[c]->dev) cudaFreeAsync(p, st);
+      pd.owners[c]->dev.clear();
     }
   }
-  if (n_items) {
+  if (pd.n_items) {
     cudaEventElapsedTime(&ctx->stats.device_ms, ctx->ev0, ctx->ev1);
     cudaEventElapsedTime(&ctx->stats.main_kernel_ms, ctx->ev_m0, ctx->ev_m1);
-    if (any_fixed) cudaEventElapsedTime(&ctx->stats.lz4_kernel_ms, ctx->ev_lz0, ctx->ev_lz1);
+    if (pd.any_fixed) cudaEventElapsedTime(&ctx->stats.lz4_kernel_ms, ctx->ev_lz0, ctx->ev_lz1);
+    if (pd.any_fixed) cudaEventElapsedTime(&ctx->stats.light_kernel_ms, ctx->ev_l0, ctx->ev_l1);
   }
-
   int32_t first_err = SB_OK;
-  const int32_t *h_status = reinterpret_cast<const int32_t *>(hT + off_status);
-  const uint32_t *h_counters = reinterpret_cast<const uint32_t *>(hT + off_counters);
-  if (n_items)
-  {
+  const uint8_t *hT = static_cast<const uint8_t *>(ctx->h_tables);
+  const int32_t *h_status = reinterpret_cast<const int32_t *>(hT + pd.off_status);
+  const uint32_t *h_counters = reinterpret_cast<const uint32_t *>(hT + pd.off_counters);
+  if (pd.n_items) {
     for (int i = 0; i < 32; ++i) ctx->stats.codec_pages[i] = h_counters[5 + i];
     std::memcpy(&ctx->stats.lz4_bytes, h_counters + 38, 8);
   }
-  pi = 0;
+  uint64_t pi = 0;
   for (uint64_t c = 0; c < n_cols; ++c) {
     sb_column_out &o = outs[c];
-    o._owner = owners[c];
-    int32_t *ps = static_cast<int32_t *>(std::malloc(sizeof(int32_t) * std::max<uint64_t>(1, cols[c].n_pages)));
-    owners[c]->host_malloc.push_back(ps);
+    o._owner = pd.owners[c];
+    int32_t *ps = static_cast<int32_t *>(std::malloc(sizeof(int32_t) * std::max<uint64_t>(1, pd.col_pages[c])));
+    pd.owners[c]->host_malloc.push_back(ps);
     o.page_status = ps;
-    for (uint64_t p = 0; p < cols[c].n_pages; ++p, ++pi) {
+    for (uint64_t p = 0; p < pd.col_pages[c]; ++p, ++pi) {
       ps[p] = h_status[pi];
       if (ps[p] != SB_OK && first_err == SB_OK) {
         first_err = ps[p];
@@ -1098,18 +1297,51 @@ int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols
       }
     }
   }
-  ctx->stats.host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
-  if (dbg_timing) {
-    auto ms = [](auto a, auto b) { return std::chrono::duration<float, std::milli>(b - a).count(); };
-    std::fprintf(stderr, "[sb timing] plan %.3f  submit %.3f  wait %.3f  finish %.3f  (device %.3f) ms\n", ms(t_host0, t_planned),
-                 ms(t_planned, t_submitted), ms(t_submitted, t_synced), ms(t_synced, std::chrono::steady_clock::now()), ctx->stats.device_ms);
-  }
-  ctx->stats.pages = n_pages_total;
-  ctx->stats.bytes_in = bytes_in;
-  ctx->stats.bytes_out = bytes_out;
+  ctx->stats.host_ms = float(now_ms() - pd.t_host0);
+  static const bool dbg_timing = std::getenv("SB_TIMING") != nullptr; // diagnostic: host phases of the call on stderr
+  if (dbg_timing)
+    std::fprintf(stderr, "[sb timing] plan %.3f  submit %.3f  wait %.3f  finish %.3f  (device %.3f) ms\n", pd.t_planned - pd.t_host0,
+                 pd.t_submitted - pd.t_planned, t_synced - pd.t_submitted, now_ms() - t_synced, ctx->stats.device_ms);
+  ctx->stats.pages = pd.n_pages_total;
+  ctx->stats.bytes_in = pd.bytes_in;
+  ctx->stats.bytes_out = pd.bytes_out;
+  pd.owners.clear();
   return first_err;
-#undef SB_TRY
-#undef SB_TRY_CUDA
+}
+
+extern "C" {
+
+int32_t sb_decode_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, int32_t out_mem, sb_column_out *outs) {
+  const int32_t rc = decode_submit(ctx, cols, n_cols, out_mem, outs, nullptr, nullptr);
+  return rc != SB_OK ? rc : sb_decode_finish_pending(ctx);
+}
+
+int32_t sb_decode_columns_into(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, int32_t out_mem, const sb_out_buffers *bufs,
+                               sb_column_out *outs) {
+  const int32_t rc = decode_submit(ctx, cols, n_cols, out_mem, outs, bufs, nullptr);
+  return rc != SB_OK ? rc : sb_decode_finish_pending(ctx);
+}
+
+int32_t sb_decode_columns_async(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, int32_t out_mem, const sb_out_buffers *bufs,
+                                sb_column_out *outs) {
+  return decode_submit(ctx, cols, n_cols, out_mem, outs, bufs, nullptr);
+}
+
+int32_t sb_decode_wait(sb_ctx *ctx) {
+  if (!ctx) return SB_CUDA;
+  return sb_decode_finish_pending(ctx);
+}
+
+int32_t sb_decode_ready(sb_ctx *ctx) {
+  if (!ctx) return SB_CUDA;
+  if (!ctx->pending.active) return 1;
+  cudaSetDevice(ctx->device);
+  return cudaStreamQuery(ctx->stream) == cudaSuccess ? 1 : 0;
+}
+
+int32_t sb_plan_columns(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_cols, sb_column_sizes *sizes) {
+  if (!sizes) return ctx ? fail(ctx, SB_INVALID_ARG, "sizes is NULL") : SB_CUDA;
+  return decode_submit(ctx, cols, n_cols, SB_MEM_DEVICE, nullptr, nullptr, sizes);
 }
 
 int32_t sb_decode_pages(sb_ctx *ctx, const sb_column_in *pages, uint64_t n_pages, int32_t out_mem, sb_column_out *outs) {

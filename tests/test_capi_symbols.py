@@ -51,7 +51,7 @@ def test_ctypes_mirror_matches_the_header(tmp_path):
     from strawboat_b200 import _capi
     structs = {"sb_page_meta": _capi.PageMeta, "sb_leaf": _capi.Leaf, "sb_column_in": _capi.ColumnIn, "sb_column_out": _capi.ColumnOut,
                "sb_stats": _capi.Stats, "sb_write_options": _capi.WriteOptions, "sb_leaf_array": _capi.LeafArray,
-               "sb_encoded_column": _capi.EncodedColumn, "sb_page_info": _capi.PageInfo, "sb_gather_stats": _capi.GatherStats, "sb_nested_level": _capi.NestedLevel,
+               "sb_encoded_column": _capi.EncodedColumn, "sb_page_info": _capi.PageInfo, "sb_gather_stats": _capi.GatherStats, "sb_out_buffers": _capi.OutBuffers, "sb_column_sizes": _capi.ColumnSizes, "sb_nested_level": _capi.NestedLevel,
                "sb_field": _capi.Field, "struct ArrowArray": _capi.ArrowArray, "struct ArrowSchema": _capi.ArrowSchema}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "strawboat_b200.h"', 'int main(void) {']
     for cname, cls in structs.items():
