@@ -206,15 +206,14 @@ def section_north_star(ctx, torch, sb, peak):
                 check_roundtrip(ctx, sb, [c])
             dev, keep = to_device_cols(torch, sb, [c], copies=ncols)  # distinct device copies: no L2 help between columns
             bc = timed_decode(ctx, dev, key="device_ms", reps=10)
-            # the kernel that decodes these pages: the light kernel for fixed-width plain pages, the full one for utf8
-            kkey = "main_kernel_ms" if t == sb.BINARY else "light_kernel_ms"
-            bk = {"main_kernel_ms": bc[kkey]}
+            # the decode kernel that did the work (the light instantiation only runs with SB_SPLIT=1)
+            bk = {"main_kernel_ms": max(bc["main_kernel_ms"], bc["light_kernel_ms"])}
             alg = bc["bytes_in"] + bc["bytes_out"]
             out.append({"case": name, "rows": rows, "columns": ncols, "pages": len(enc.metas) * ncols, "algorithmic_bytes": alg,
                         "call_device_us": round(bc["device_ms"] * 1e3, 1), "kernel_us": round(bk["main_kernel_ms"] * 1e3, 1),
                         "call_gbs": round(alg / bc["device_ms"] / 1e6, 1), "kernel_gbs": round(alg / bk["main_kernel_ms"] / 1e6, 1),
                         "frac_call": round(alg / bc["device_ms"] / 1e6 / peak, 3), "frac_kernel": round(alg / bk["main_kernel_ms"] / 1e6 / peak, 3),
-                        "kernel": "sb_decode_kernel" if t == sb.BINARY else "sb_decode_light_kernel", "launches": bc["kernel_launches"]})
+                        "launches": bc["kernel_launches"]})
             del dev, keep
     return {"target": "north_star: >= 0.60 of the HBM peak on 1 M-row i64 / f64 / utf8 page decode", "peak_gbs": peak,
             "pages_written_by": "strawboat_b200 GPU encoder, default_compression None, adaptive off", "cases": out}

@@ -39,7 +39,7 @@ struct DecodePending { // a submitted decode call whose results have not been co
   std::vector<Owner *> owners;
   std::vector<uint64_t> col_pages;
   size_t off_status = 0, off_counters = 0;
-  bool any_fixed = false;
+  bool any_fixed = false, split = false;
   uint64_t bytes_in = 0, bytes_out = 0;
   double t_host0 = 0, t_planned = 0, t_submitted = 0;
 };

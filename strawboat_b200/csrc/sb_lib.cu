@@ -114,80 +114,76 @@ __device__ __forceinline__ bool light_codec_tree(const uint8_t *h, uint32_t avai
   return false;
 }
 
-__global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, uint32_t n_pages,
-                                   Lz4Job *jobs, uint32_t *n_jobs, uint8_t *side_flags, const PageAux *__restrict__ aux, uint32_t light_cap) {
-  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= n_pages) return;
-  const PageDesc pg = pages[i];
-  const ColDesc col = cols[pg.col];
+// Returns the page's flags: low bits = side (0 decode kernel, 1 sb_lz4_kernel, 2 stored LZ4 block, 3 plain page),
+// SB_FLAG_HEAVY = not for the light decode kernel.  One warp per page (uniform control flow: every lane loads the
+// same bytes); the family test only runs for pages that are neither plain nor LZ4.
+__device__ __forceinline__ uint8_t classify_page(const PageDesc &pg, const ColDesc &col, uint32_t i, uint32_t n_pages, Lz4Job *jobs, uint32_t *n_jobs,
+                                                 const PageAux *__restrict__ aux, uint32_t light_cap, uint32_t lane) {
   const bool nested = col.n_nested > 1;
-  if (!is_fixed_type(col.type) || nested) {
-    if (lane == 0) side_flags[i] = SB_FLAG_HEAVY; // binary, boolean, nested: the full kernel
-    if (!is_fixed_type(col.type)) return;
-  }
-  // flat fixed-width page: family by codec tree and staging size (pages the light kernel cannot stage stay heavy)
-  uint8_t fam = 0;
-  if (!nested) {
-    uint32_t vb0 = 0;
-    bool hdr_ok = true;
-    if (col.nullable) {
-      hdr_ok = pg.len >= 4;
-      const uint32_t L = hdr_ok ? ldg_u32u(pg.src) : 0;
-      hdr_ok = hdr_ok && L <= pg.len - 4;
-      vb0 = 4 + L;
-    }
-    const bool small = pg.len + 32 <= light_cap;
-    fam = (hdr_ok && small && light_codec_tree(pg.src + vb0, pg.len - vb0)) ? 0 : SB_FLAG_HEAVY;
-  } else {
-    fam = SB_FLAG_HEAVY;
-  }
+  if (!is_fixed_type(col.type)) return SB_FLAG_HEAVY; // binary, boolean: the full kernel
   uint32_t vb, clen;
   uint64_t n_vals = pg.num_values;
   const uint8_t *body = pg.src;
   uint32_t body_len = pg.len;
   if (nested) {
     // [u32 rows][u32 rep_len][u32 def_len][rep][def][VALUE_BLOCK over the leaf slots]: the plan pass counted the slots
-    if (pg.len < 12 || pg.aux == 0xffffffffu) return;
+    if (pg.len < 12 || pg.aux == 0xffffffffu) return SB_FLAG_HEAVY;
     const uint64_t lv = 12ull + ldg_u32u(pg.src + 4) + ldg_u32u(pg.src + 8);
-    if (lv > pg.len) return;
+    if (lv > pg.len) return SB_FLAG_HEAVY;
     body += lv;
     body_len -= uint32_t(lv);
     n_vals = aux[pg.aux].cnt[col.n_nested - 1];
   } else if (plain_page(pg.src, pg.len, col.nullable != 0, uint64_t(pg.num_values) * uint32_t(col.W))) {
     // plain pages stream through the TMA ring whatever their size: light unless the validity section needs a large stage
     const uint32_t stage = pg.len - pg.num_values * uint32_t(col.W);
-    if (lane == 0) side_flags[i] = 3 | ((!col.nullable || stage + 32 <= light_cap) ? 0 : SB_FLAG_HEAVY);
-    return;
+    return 3 | ((!col.nullable || stage + 32 <= light_cap) ? 0 : SB_FLAG_HEAVY);
   }
   if (!lz4_side_page(body, body_len, !nested && col.nullable != 0, &vb, &clen)) {
-    if (lane == 0) side_flags[i] = fam;
-    return;
+    if (nested) return SB_FLAG_HEAVY;
+    // flat fixed-width page: family by codec tree and staging size (pages the light kernel cannot stage stay heavy)
+    uint32_t vb0 = 0;
+    if (col.nullable) {
+      if (pg.len < 4) return SB_FLAG_HEAVY;
+      const uint32_t L = ldg_u32u(pg.src);
+      if (L > pg.len - 4) return SB_FLAG_HEAVY;
+      vb0 = 4 + L;
+    }
+    return (pg.len + 32 <= light_cap && light_codec_tree(pg.src + vb0, pg.len - vb0)) ? 0 : SB_FLAG_HEAVY;
   }
   const uint64_t dlen64 = n_vals * uint32_t(col.W);
-  if (dlen64 > SB_LZ4_MAXPOS / 2 || clen > SB_LZ4_MAXPOS / 2) { // positions are 30-bit in sb_lz4_kernel: decoded in the full kernel
-    if (lane == 0) side_flags[i] = SB_FLAG_HEAVY;
-    return;
-  }
+  if (dlen64 > SB_LZ4_MAXPOS / 2 || clen > SB_LZ4_MAXPOS / 2) return SB_FLAG_HEAVY; // positions are 30-bit in sb_lz4_kernel
   const uint32_t dlen = uint32_t(dlen64);
   // an LZ4 page leaves the validity section (if any) to the decode kernel: light when that stages small
   const uint8_t lz_fam = nested ? SB_FLAG_HEAVY : ((!col.nullable || vb + 32 <= light_cap) ? 0 : SB_FLAG_HEAVY);
-  if (lz4_stored_block(body + vb + 9, clen, dlen)) {
-    if (lane == 0) side_flags[i] = 2 | (nested || pg.len + 32 > light_cap ? SB_FLAG_HEAVY : lz_fam);
-    return;
+  if (lz4_stored_block(body + vb + 9, clen, dlen)) return 2 | (nested || pg.len + 32 > light_cap ? SB_FLAG_HEAVY : lz_fam);
+  if (lane == 0) {
+    Lz4Job j;
+    j.src = body + vb + 9;
+    j.dst = col.values + pg.out_elem * uint64_t(col.W);
+    j.clen = clen;
+    j.dlen = dlen;
+    j.page = i;
+    j.pad = 0;
+    // n_jobs[0] = long jobs (front), n_jobs[1] = short jobs (back)
+    const bool big = clen >= 8192;
+    const uint32_t slot = big ? atomicAdd(n_jobs, 1u) : n_pages - 1 - atomicAdd(n_jobs + 1, 1u);
+    jobs[slot] = j;
   }
-  if (lane != 0) return;
-  Lz4Job j;
-  j.src = body + vb + 9;
-  j.dst = col.values + pg.out_elem * uint64_t(col.W);
-  j.clen = clen;
-  j.dlen = dlen;
-  j.page = i;
-  j.pad = 0;
-  // n_jobs[0] = long jobs (front), n_jobs[1] = short jobs (back)
-  const bool big = clen >= 8192;
-  uint32_t slot = big ? atomicAdd(n_jobs, 1u) : n_pages - 1 - atomicAdd(n_jobs + 1, 1u);
-  jobs[slot] = j;
-  side_flags[i] = 1 | lz_fam;
+  return 1 | lz_fam;
+}
+
+__global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, uint32_t n_pages,
+                                   Lz4Job *jobs, uint32_t *n_jobs, uint8_t *side_flags, const PageAux *__restrict__ aux, uint32_t light_cap,
+                                   uint32_t *n_heavy) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n_pages) return;
+  const PageDesc pg = pages[i];
+  const ColDesc col = cols[pg.col];
+  const uint8_t f = classify_page(pg, col, i, n_pages, jobs, n_jobs, aux, light_cap, lane);
+  if (lane == 0) {
+    if (f) side_flags[i] = f; // the array was zeroed with the tables
+    if (n_heavy && (f & SB_FLAG_HEAVY)) atomicAdd(n_heavy, 1u);
+  }
 }
 
 // One CTA = SB_LZ4_PAIRS scanner warps (warps 0..PAIRS-1, one warpgroup) + as many mover warps (the next
@@ -494,7 +490,9 @@ __device__ __forceinline__ void decode_body(const PageDesc *__restrict__ pages, 
 __global__ void __launch_bounds__(SB_NT, 4)
     sb_decode_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, const WorkItem *__restrict__ items, uint32_t n_items,
                      uint32_t *counter, uint8_t *scratch, uint64_t scratch_per_cta, int32_t *status, uint32_t stage_cap, uint32_t smem_bytes,
-                     const uint8_t *__restrict__ side_flags, PageAux *aux, BinEntry *entries, uint32_t *codec_hist, int pass, int split) {
+                     const uint8_t *__restrict__ side_flags, PageAux *aux, BinEntry *entries, uint32_t *codec_hist, int pass, int split,
+                     const uint32_t *__restrict__ n_heavy) {
+  if (split && n_heavy && *n_heavy == 0) return; // every page went to the light kernel
   decode_body<false>(pages, cols, items, n_items, counter, scratch, scratch_per_cta, status, stage_cap, smem_bytes, side_flags, aux, entries,
                      codec_hist, pass, split != 0);
 }
@@ -841,7 +839,7 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
 
   // one pinned staging buffer, mirrored on the device:
   //   uploaded : [ColDesc * n_cols][PageDesc * P][WorkItem * I][WorkItem * plan][PageAux * plan]
-  //   zeroed   : [status * P][counters * 40][side_flags * P]      device only: [Lz4Job * P]
+  //   zeroed   : [status * P][counters * 48][side_flags * P]      device only: [Lz4Job * P]
   size_t off_cols = 0;
   size_t off_pages = align_up(off_cols + sizeof(ColDesc) * n_cols, 16);
   size_t off_items = align_up(off_pages + sizeof(PageDesc) * n_pages_total, 16);
@@ -850,7 +848,7 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
   size_t tables_bytes = align_up(off_aux + sizeof(PageAux) * n_plan, 16);
   size_t off_status = tables_bytes;
   size_t off_counters = align_up(off_status + sizeof(int32_t) * n_pages_total, 16);
-  size_t off_flags = off_counters + 40 * 4;
+  size_t off_flags = off_counters + 48 * 4;
   size_t zero_end = align_up(off_flags + n_pages_total, 16);
   size_t off_jobs = zero_end;
   size_t dev_bytes = off_jobs + sizeof(Lz4Job) * n_pages_total;
@@ -1011,23 +1009,37 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
   const ColDesc *d_cols = reinterpret_cast<const ColDesc *>(dT + off_cols);
   int32_t *d_status = reinterpret_cast<int32_t *>(dT + off_status);
   // counters: [0] main queue, [1] lz4 queue, [2] long lz4 jobs, [3] short lz4 jobs, [4] plan queue,
-  //           [5..36] pages per top-level codec, [38..39] u64 bytes handled by sb_lz4_kernel
+  //           [5..36] pages per top-level codec, [37] light queue, [38..39] u64 bytes handled by sb_lz4_kernel,
+  //           [40] pages of the full kernel's family (sb_classify_kernel)
   uint32_t *d_counters = reinterpret_cast<uint32_t *>(dT + off_counters);
   uint8_t *d_flags = dT + off_flags;
   Lz4Job *d_jobs = reinterpret_cast<Lz4Job *>(dT + off_jobs);
   PageAux *d_aux = reinterpret_cast<PageAux *>(dT + off_aux);
   BinEntry *d_entries = static_cast<BinEntry *>(ctx->d_entries.p);
   const auto t_planned = std::chrono::steady_clock::now();
-  uint32_t grid_light = 0;
-  if (any_fixed && n_items) {
+  // Light / full split of the decode kernel (SB_SPLIT=1; OFF by default).  Measured on B200 (profiles/README.md, round 2):
+  // the light instantiation (64 registers) makes Dict / RLE pages of a column decoded alone ~20 % faster at 8 CTAs per
+  // SM, but next to the LZ4 kernel (161 KiB of shared memory per SM) and the full kernel (74 KiB per CTA) the three do
+  // not co-reside; at the 5 + 2 CTAs per SM that do fit, plain pages lose their 32 KiB TMA ring and the step gets slower
+  // (config 2: 362 -> 297 GB/s).  Kept selectable for experiments; the default is one kernel at its own occupancy.
+  static const bool want_split = std::getenv("SB_SPLIT") != nullptr;
+  bool fixed_only = any_fixed && want_split;
+  for (uint64_t c = 0; c < n_cols; ++c) fixed_only = fixed_only && fixed_type(cols[c].leaf.type) && !col_nested(cols[c]);
+  const bool split = fixed_only && n_items > 0;
+  uint32_t grid_light = 0, smem_heavy = smem;
+  if (split) {
     if (ctx->light_occ == 0) {
       int q = 1;
       SB_TRY_CUDA(cudaFuncSetAttribute(sb_decode_light_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       SB_TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, sb_decode_light_kernel, SB_NT, kLightSmem));
       ctx->light_occ = std::max(1, q);
     }
-    grid_light = uint32_t(std::min<uint64_t>(n_items, uint64_t(ctx->sm_count) * ctx->light_occ));
+    grid_light = uint32_t(std::min<uint64_t>(n_items, uint64_t(ctx->sm_count) * std::min(ctx->light_occ, 5)));
+    // 5 x 26 KiB + 2 x 40 KiB per SM: the full kernel stages pages up to 34 KiB here and reads larger ones in place
+    smem_heavy = std::min<uint32_t>(smem, 40 * 1024);
+    grid = uint32_t(std::min<uint64_t>(grid, uint64_t(ctx->sm_count) * 2));
   }
+  const uint32_t stage_cap_heavy = split ? smem_heavy - kArenaMin : stage_cap;
   if (n_items) {
     SB_TRY(dev_reserve(ctx, ctx->d_scratch, scratch_per_cta * (uint64_t(grid) + grid_light)));
     SB_TRY_CUDA(cudaMemcpyAsync(dT, hT, tables_bytes, cudaMemcpyHostToDevice, st));
@@ -1040,7 +1052,7 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
     uint32_t grid0 = uint32_t(std::min<uint64_t>(n_plan, uint64_t(ctx->sm_count) * occ));
     sb_decode_kernel<<<grid0, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items0), uint32_t(n_plan),
                                                  d_counters + 4, static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta, d_status,
-                                                 stage_cap, smem, nullptr, d_aux, d_entries, d_counters + 5, 0, 0);
+                                                 stage_cap, smem, nullptr, d_aux, d_entries, d_counters + 5, 0, 0, nullptr);
     SB_TRY_CUDA(cudaGetLastError());
     ctx->stats.kernel_launches += 1;
     SB_TRY_CUDA(cudaMemcpyAsync(h_aux, d_aux, sizeof(PageAux) * n_plan, cudaMemcpyDeviceToHost, st));
@@ -1136,7 +1148,8 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_fork, st));
       SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
       sb_classify_kernel<<<uint32_t((n_pages_total + 7) / 8), 256, 0, ctx->aux>>>(d_pages, d_cols, uint32_t(n_pages_total), d_jobs,
-                                                                                    d_counters + 2, d_flags, d_aux, kLightSmem - kArenaMin);
+                                                                                    d_counters + 2, d_flags, d_aux, kLightSmem - kArenaMin,
+                                                                                    split ? d_counters + 40 : nullptr);
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_cls, ctx->aux));
       if (ctx->lz4_occ == 0) {
         int q = 1;
@@ -1153,7 +1166,7 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
       ctx->stats.kernel_launches += 2;
     }
-    if (any_fixed) {
+    if (split) {
       // the light kernel (flat fixed-width pages with light codec trees) on its own stream, next to the full one
       SB_TRY_CUDA(cudaStreamWaitEvent(ctx->aux2, ctx->ev_cls, 0));
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_l0, ctx->aux2));
@@ -1165,19 +1178,17 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_l1, ctx->aux2));
       SB_TRY_CUDA(cudaEventRecord(ctx->ev_join2, ctx->aux2));
       ctx->stats.kernel_launches += 1;
-      SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_cls, 0));
     }
+    if (any_fixed) SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_cls, 0));
     SB_TRY_CUDA(cudaEventRecord(ctx->ev_m0, st));
-    sb_decode_kernel<<<grid, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items),
+    sb_decode_kernel<<<grid, SB_NT, smem_heavy, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items),
                                                 uint32_t(n_items), d_counters, static_cast<uint8_t *>(ctx->d_scratch.p),
-                                                scratch_per_cta, d_status, stage_cap, smem, any_fixed ? d_flags : nullptr, d_aux,
-                                                d_entries, d_counters + 5, 1, any_fixed ? 1 : 0);
+                                                scratch_per_cta, d_status, stage_cap_heavy, smem_heavy, any_fixed ? d_flags : nullptr, d_aux,
+                                                d_entries, d_counters + 5, 1, split ? 1 : 0, d_counters + 40);
     SB_TRY_CUDA(cudaGetLastError());
     SB_TRY_CUDA(cudaEventRecord(ctx->ev_m1, st));
-    if (any_fixed) {
-      SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-      SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
-    }
+    if (any_fixed) SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (split) SB_TRY_CUDA(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
     SB_TRY_CUDA(cudaEventRecord(ctx->ev1, st));
     ctx->stats.kernel_launches += 1;
     // statuses + codec histogram back (pinned), reuse the tail of the host table buffer
@@ -1236,6 +1247,7 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
   pd.off_status = off_status;
   pd.off_counters = off_counters;
   pd.any_fixed = any_fixed;
+  pd.split = split;
   pd.bytes_in = bytes_in;
   pd.bytes_out = bytes_out;
   pd.t_host0 = t_host0;
@@ -1272,7 +1284,7 @@ int32_t sb_decode_finish_pending(sb_ctx *ctx) {
     cudaEventElapsedTime(&ctx->stats.device_ms, ctx->ev0, ctx->ev1);
     cudaEventElapsedTime(&ctx->stats.main_kernel_ms, ctx->ev_m0, ctx->ev_m1);
     if (pd.any_fixed) cudaEventElapsedTime(&ctx->stats.lz4_kernel_ms, ctx->ev_lz0, ctx->ev_lz1);
-    if (pd.any_fixed) cudaEventElapsedTime(&ctx->stats.light_kernel_ms, ctx->ev_l0, ctx->ev_l1);
+    if (pd.split) cudaEventElapsedTime(&ctx->stats.light_kernel_ms, ctx->ev_l0, ctx->ev_l1);
   }
   int32_t first_err = SB_OK;
   const uint8_t *hT = static_cast<const uint8_t *>(ctx->h_tables);
