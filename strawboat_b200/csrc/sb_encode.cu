@@ -201,9 +201,9 @@ __device__ uint32_t enc_levels(const uint32_t *lv, uint32_t n, uint32_t w, uint8
   return ul + groups * w;
 }
 
-constexpr uint32_t kEncSmem = 48 * 1024;
+constexpr uint32_t kEncSmem = 56 * 1024; // 4 CTAs per SM: the 8192-slot distinct table of a page (32 + 16 KiB), or the LZ tables
 
-__global__ void __launch_bounds__(SB_NT)
+__global__ void __launch_bounds__(SB_NT, 4)
     sb_encode_kernel(const EncPage *__restrict__ pages, const EncCol *__restrict__ cols, uint32_t n_pages, uint32_t *counter,
                      uint8_t *slab, uint8_t *scratch, uint64_t scratch_per_cta, uint32_t *page_len, int32_t *status, EOpts base,
                      uint32_t *codec_hist) {

@@ -170,8 +170,12 @@ struct EffFixed {
     return s == kNone ? lead : v.get(s);
   }
   __device__ __forceinline__ uint32_t hash(uint32_t i) const {
-    uint64_t k = key(i) * 0x9E3779B97F4A7C15ull;
-    return uint32_t(k >> 32) ^ uint32_t(k);
+    // doubles that hold small integers differ only in their top 20-odd bits: fold the halves before the
+    // multiply and keep the product's HIGH bits, the ones every input bit reaches
+    uint64_t k = key(i);
+    k = (k ^ (k >> 32)) * 0x9E3779B97F4A7C15ull;
+    k = (k ^ (k >> 29)) * 0xBF58476D1CE4E5B9ull;
+    return uint32_t(k >> 32);
   }
   __device__ __forceinline__ bool equal(uint32_t i, uint32_t j) const { return key(i) == key(j); }
   __device__ __forceinline__ void put(uint8_t *out, uint32_t i, int W) const { st_le(out, key(i), W); }
@@ -183,8 +187,15 @@ struct EffFixed {
 // exact counts below n/3, see Dict / Freq ratios).  slot_of (optional) receives each row's slot.
 // ------------------------------------------------------------------------------------
 struct HashTab {
-  uint32_t *rep, *cnt, *first;
+  uint32_t *rep, *cnt; // rep: 1 + the FIRST row holding the slot's key (0 = empty); cnt: rows with that key
   uint32_t mask;
+  uint32_t cnt16;      // counts packed two per word (pages below 65536 rows): half the shared memory
+  __device__ __forceinline__ uint32_t first(uint32_t h) const { return rep[h] - 1; }
+  __device__ __forceinline__ uint32_t count(uint32_t h) const { return cnt16 ? (cnt[h >> 1] >> (16 * (h & 1))) & 0xffffu : cnt[h]; }
+  __device__ __forceinline__ void add(uint32_t h, uint32_t c) {
+    if (cnt16) atomicAdd(cnt + (h >> 1), c << (16 * (h & 1)));
+    else atomicAdd(cnt + h, c);
+  }
 };
 __device__ __forceinline__ uint32_t hash_cap(uint32_t limit) {
   uint64_t want = 2ull * limit + 2 * SB_NT + 16;
@@ -192,48 +203,62 @@ __device__ __forceinline__ uint32_t hash_cap(uint32_t limit) {
   while (cap < want && cap < 0x80000000u) cap <<= 1;
   return cap;
 }
+// The table lives in shared memory when it fits (8192 slots x 8 bytes for an 8192-row page): every row costs a
+// shared-memory probe, one key compare and -- aggregated over the lanes of a warp that landed on the same slot --
+// one shared-memory atomic.
 template <class Acc>
-__device__ uint32_t hash_distinct(Dctx &cx, const Acc &acc, uint32_t n, uint32_t limit, HashTab *t, uint32_t *slot_of) {
+__device__ uint32_t hash_distinct(Dctx &cx, const Acc &acc, uint32_t n, uint32_t limit, HashTab *t, uint32_t *slot_of, bool compact = false) {
   const uint32_t cap = hash_cap(limit);
+  t->cnt16 = compact && n < 65536u; // callers that reuse cnt[] as a slot -> id map keep full words
   t->rep = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(cap) * 4));
-  t->cnt = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(cap) * 4));
-  t->first = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(cap) * 4));
+  t->cnt = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(cap) * (t->cnt16 ? 2 : 4)));
   t->mask = cap - 1;
-  if (!t->rep || !t->cnt || !t->first) {
+  if (!t->rep || !t->cnt) {
     cx.flag(SB_NYI);
     return kNone;
   }
   for (uint32_t i = threadIdx.x; i < cap; i += SB_NT) {
     t->rep[i] = 0;
-    t->cnt[i] = 0;
-    t->first[i] = kNone;
+    if (!t->cnt16 || i < cap / 2) t->cnt[i] = 0;
   }
   volatile int *ctr = cx.bcast; // [0] distinct keys, [1] overflow flag
   __syncthreads();
   if (threadIdx.x == 0) cx.bcast[0] = cx.bcast[1] = 0;
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n; i += SB_NT) {
-    uint32_t h = acc.hash(i) & t->mask;
-    for (;;) {
-      if (ctr[1]) break;
-      uint32_t r = *reinterpret_cast<volatile uint32_t *>(t->rep + h);
-      if (r == 0) {
-        uint32_t old = atomicCAS(t->rep + h, 0u, i + 1);
-        if (old == 0) {
-          r = i + 1;
-          if (uint32_t(atomicAdd(cx.bcast, 1)) >= limit) atomicExch(cx.bcast + 1, 1);
-        } else {
-          r = old;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t h_next = threadIdx.x < n ? acc.hash(threadIdx.x) : 0u;
+  for (uint32_t i0 = 0; i0 < n; i0 += SB_NT) { // warp-uniform trip count: the lanes vote on their slots below
+    const uint32_t i = i0 + threadIdx.x;
+    uint32_t h = kNone;
+    const uint32_t h_cur = h_next;
+    if (i + SB_NT < n) h_next = acc.hash(i + SB_NT); // the next row's key load travels under this row's probes
+    if (i < n) {
+      h = h_cur & t->mask;
+      for (;;) {
+        if (ctr[1]) {
+          h = kNone;
+          break;
         }
+        uint32_t r = *reinterpret_cast<volatile uint32_t *>(t->rep + h);
+        if (r == 0) {
+          const uint32_t old = atomicCAS(t->rep + h, 0u, i + 1);
+          if (old == 0) {
+            r = i + 1;
+            if (uint32_t(atomicAdd(cx.bcast, 1)) >= limit) atomicExch(cx.bcast + 1, 1);
+          } else {
+            r = old;
+          }
+        }
+        if (r - 1 == i || acc.equal(r - 1, i)) {
+          if (i + 1 < r) atomicMin(t->rep + h, i + 1); // the representative is replaced by an equal key: probes stay valid
+          if (slot_of) slot_of[i] = h;
+          break;
+        }
+        h = (h + 1) & t->mask;
       }
-      if (r - 1 == i || acc.equal(r - 1, i)) {
-        atomicAdd(t->cnt + h, 1u);
-        atomicMin(t->first + h, i);
-        if (slot_of) slot_of[i] = h;
-        break;
-      }
-      h = (h + 1) & t->mask;
     }
+    const uint32_t peers = __match_any_sync(0xffffffffu, h);
+    if (h != kNone && lane == uint32_t(__ffs(peers) - 1)) t->add(h, uint32_t(__popc(peers)));
   }
   __syncthreads();
   uint32_t distinct = uint32_t(cx.bcast[0]);
@@ -241,12 +266,25 @@ __device__ uint32_t hash_distinct(Dctx &cx, const Acc &acc, uint32_t n, uint32_t
   __syncthreads();
   return ovf ? kNone : distinct;
 }
+// slot of every row in a table built over the same keys (read-only probes)
+template <class Acc> __device__ void hash_lookup(const Acc &acc, uint32_t n, const HashTab &t, uint32_t *slot_of) {
+  for (uint32_t i = threadIdx.x; i < n; i += SB_NT) {
+    uint32_t h = acc.hash(i) & t.mask;
+    for (;;) {
+      const uint32_t r = t.rep[h];
+      if (r == 0 || r - 1 == i || acc.equal(r - 1, i)) break; // r == 0 cannot happen for a key of the build set
+      h = (h + 1) & t.mask;
+    }
+    slot_of[i] = h;
+  }
+  __syncthreads();
+}
 // (max count, earliest first row) over the table
 __device__ void hash_top(Dctx &cx, const HashTab &t, uint32_t *max_count, uint32_t *first_row) {
   uint64_t best = 0;
   for (uint32_t h = threadIdx.x; h <= t.mask; h += SB_NT)
     if (t.rep[h]) {
-      uint64_t k = (uint64_t(t.cnt[h]) << 32) | uint64_t(kNone - t.first[h]);
+      uint64_t k = (uint64_t(t.count(h)) << 32) | uint64_t(kNone - t.first(h));
       best = k > best ? k : best;
     }
   best = block_max_u64(cx, best);
@@ -264,8 +302,24 @@ __device__ __forceinline__ uint32_t ld4(const uint8_t *p) {
   return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
 }
 __device__ __forceinline__ uint32_t lz4_len_bytes(uint32_t len) { return len < 15 ? 0 : 1 + (len - 15) / 255; } // extension bytes
-__device__ uint32_t lz4_emit_seq(uint8_t *out, uint32_t op, const uint8_t *lit, uint32_t nlit, uint32_t offset, uint32_t ml /*0: last*/) {
+// literal runs: bytes below 64, 16-byte vectors (aligned on dst) above
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n) {
   const uint32_t lane = threadIdx.x & 31;
+  if (n < 64) {
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    return;
+  }
+  const uint32_t head = uint32_t((16 - (uintptr_t(dst) & 15)) & 15);
+  if (lane < head) dst[lane] = src[lane];
+  const uint32_t nv = (n - head) >> 4;
+  for (uint32_t v = lane; v < nv; v += 32) *reinterpret_cast<uint4 *>(dst + head + 16 * v) = ld_u128u(src + head + 16 * v);
+  for (uint32_t i = head + 16 * nv + lane; i < n; i += 32) dst[i] = src[i];
+}
+// One sequence, written by a warp.  The returned position is a pure function of the arguments, so the join phase
+// of lz_compress_cta calls it from every warp with `hdr` true on one of them and copies the literals block-wide.
+__device__ __forceinline__ uint32_t lz4_emit_seq(uint8_t *out, uint32_t op, const uint8_t *lit, uint32_t nlit, uint32_t offset, uint32_t ml /*0: last*/,
+                                 bool hdr = true, bool copy_lit = true) {
+  const uint32_t lane = hdr ? threadIdx.x & 31 : 1u; // lane 0 of the writing warp stores the token / length / offset bytes
   uint32_t mlc = ml ? ml - 4 : 0;
   if (lane == 0) {
     out[op] = uint8_t((min(nlit, 15u) << 4) | min(mlc, 15u));
@@ -280,7 +334,7 @@ __device__ uint32_t lz4_emit_seq(uint8_t *out, uint32_t op, const uint8_t *lit, 
     }
   }
   uint32_t q = op + 1 + lz4_len_bytes(nlit);
-  for (uint32_t i = lane; i < nlit; i += 32) out[q + i] = lit[i];
+  if (copy_lit) warp_copy(out + q, lit, nlit);
   q += nlit;
   if (ml) {
     if (lane == 0) {
@@ -304,8 +358,9 @@ __device__ uint32_t lz4_emit_seq(uint8_t *out, uint32_t op, const uint8_t *lit, 
 // Snappy raw elements for one (literal run, match) pair (basic.rs:138-152 -> snap::raw::Encoder; compressed bytes
 // are implementation defined, any valid stream decodes with snap::raw::Decoder): a literal element, then copy
 // elements with a 16-bit offset (1..64 bytes each; 11-bit form for 4..11 bytes at offsets < 2048).
-__device__ uint32_t snappy_emit_seq(uint8_t *out, uint32_t op, const uint8_t *lit, uint32_t nlit, uint32_t offset, uint32_t ml /*0: last*/) {
-  const uint32_t lane = threadIdx.x & 31;
+__device__ __forceinline__ uint32_t snappy_emit_seq(uint8_t *out, uint32_t op, const uint8_t *lit, uint32_t nlit, uint32_t offset, uint32_t ml /*0: last*/,
+                                    bool hdr = true, bool copy_lit = true) {
+  const uint32_t lane = hdr ? threadIdx.x & 31 : 1u;
   uint32_t q = op;
   if (nlit) {
     const uint32_t l1 = nlit - 1;
@@ -315,7 +370,7 @@ __device__ uint32_t snappy_emit_seq(uint8_t *out, uint32_t op, const uint8_t *li
       for (uint32_t k = 0; k < nb; ++k) out[q + 1 + k] = uint8_t(l1 >> (8 * k));
     }
     q += 1 + nb;
-    for (uint32_t i = lane; i < nlit; i += 32) out[q + i] = lit[i];
+    if (copy_lit) warp_copy(out + q, lit, nlit);
     q += nlit;
   }
   // copy elements: their sizes are a pure function of (offset, ml), so every lane tracks q; lane 0 writes
@@ -340,70 +395,230 @@ __device__ uint32_t snappy_emit_seq(uint8_t *out, uint32_t op, const uint8_t *li
   __syncwarp();
   return q;
 }
-constexpr uint32_t kLz4HashBits = 12;
-// greedy matcher shared by the LZ4 and the Snappy writer (the element syntax is the only difference)
+// ------------------------------------------------------------------------------------
+// Greedy LZ matcher shared by the LZ4 and the Snappy writer (the element syntax is the only difference).
+// The input is cut into up to SB_NWARP chunks, one warp each with its own hash table (positions of its chunk
+// only, so the result does not depend on warp timing).  Per step a warp probes 32 consecutive positions, every
+// lane with a verified candidate extends its own match (8 bytes per compare, capped), and the warp then walks
+// the hits left to right taking each one that starts at or after the end of the previous match -- several
+// sequences per step on data with short matches (f64 / i64 with a few significant bytes), one cooperative
+// 32-bytes-per-step extension on long ones.
+// Chunk 0 writes its sequences in place.  A later chunk w does not know where its bytes land, nor where the
+// literal run before its first match starts (the previous chunks' tail): it parks its first match in shared
+// memory, writes the rest at a temporary offset at or beyond the final one, and the join phase emits the
+// junction sequences and moves the bodies left.
+// ------------------------------------------------------------------------------------
+struct LzChunk {
+  uint32_t has_first, mp1, mc1, ml1; // first match of the chunk (chunks 1..: emitted by the join phase)
+  uint32_t body_off, body_len;       // sequences after the first one, where the warp wrote them
+  uint32_t tail;                     // first byte after the chunk's last match (its trailing literals)
+  uint32_t pad;
+};
+template <bool SNAPPY> __device__ __forceinline__ uint32_t lz_slack(uint32_t len) { return SNAPPY ? len / 32 + 32 : len / 255 + 16; }
+template <bool SNAPPY>
+__device__ __forceinline__ uint32_t lz_emit(uint8_t *out, uint32_t op, const uint8_t *lit, uint32_t nlit, uint32_t offset, uint32_t ml, bool hdr = true,
+                                            bool copy_lit = true) {
+  return SNAPPY ? snappy_emit_seq(out, op, lit, nlit, offset, ml, hdr, copy_lit) : lz4_emit_seq(out, op, lit, nlit, offset, ml, hdr, copy_lit);
+}
+// the same sequence written by the whole CTA: warp 0 stores the few header bytes, everyone copies the literals
+template <bool SNAPPY>
+__device__ uint32_t lz_emit_cta(uint8_t *out, uint32_t op, const uint8_t *lit, uint32_t nlit, uint32_t offset, uint32_t ml) {
+  uint32_t qlit;
+  if (SNAPPY) {
+    const uint32_t l1 = nlit ? nlit - 1 : 0;
+    qlit = op + (nlit ? 1 + (l1 < 60 ? 0u : l1 < (1u << 8) ? 1u : l1 < (1u << 16) ? 2u : l1 < (1u << 24) ? 3u : 4u) : 0);
+  } else {
+    qlit = op + 1 + lz4_len_bytes(nlit);
+  }
+  const uint32_t q = lz_emit<SNAPPY>(out, op, lit, nlit, offset, ml, threadIdx.x < 32, false);
+  copy_bytes(out + qlit, lit, nlit);
+  return q;
+}
+constexpr uint32_t kLzMinChunk = 2048;
+constexpr uint32_t kStageMax = 64 * 1024; // a page of 8192 eight-byte values
+constexpr uint32_t kStageKeep = 48 * 1024 + 512; // the distinct table of an 8192-row page (32 + 16 KiB)
+constexpr uint32_t kLzLaneCap = 36; // per-lane match extension stops here; longer matches continue warp-wide
+
 template <bool SNAPPY> __device__ uint32_t lz_compress_cta(Dctx &cx, const uint8_t *in, uint32_t n, uint8_t *out) {
   Arena mark = cx.ar;
-  uint32_t *tab = static_cast<uint32_t *>(cx.ar.alloc((1u << kLz4HashBits) * 4));
-  if (!tab) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t cl = ((n + SB_NWARP - 1) / SB_NWARP + 63) & ~63u;
+  cl = cl < kLzMinChunk ? kLzMinChunk : cl;
+  const uint32_t n_chunks = n ? (n + cl - 1) / cl : 1; // <= SB_NWARP
+  uint32_t bits = 11;
+  uint32_t *tabs = nullptr;
+  while (bits >= 9 && !(tabs = static_cast<uint32_t *>(cx.ar.alloc_shared(uint64_t(n_chunks) << (bits + 2))))) --bits;
+  if (!tabs) {
+    bits = 11;
+    tabs = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n_chunks) << (bits + 2)));
+  }
+  LzChunk *recs = static_cast<LzChunk *>(cx.ar.alloc(sizeof(LzChunk) * SB_NWARP));
+  if (!tabs || !recs) {
     cx.flag(SB_NYI);
     return kEncFail;
   }
-  for (uint32_t i = threadIdx.x; i < (1u << kLz4HashBits); i += SB_NT) tab[i] = kNone;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const uint32_t lane = threadIdx.x;
-    uint32_t ip = 0, anchor = 0, op = 0;
-    if (SNAPPY) { // preamble: varint of the uncompressed length
-      uint32_t v = n;
-      do {
-        if (lane == 0) out[op] = uint8_t((v & 0x7fu) | (v >> 7 ? 0x80u : 0u));
-        ++op;
-        v >>= 7;
-      } while (v);
-    }
-    const uint32_t mflimit = n >= 13 ? n - 12 : 0; // last match start (inclusive) -- LZ4 block end rules
-    const uint32_t match_end_limit = n >= 5 ? n - 5 : 0;
-    while (n >= 13 && ip <= mflimit) {
-      uint32_t p = ip + lane;
-      bool in_range = p <= mflimit;
+  uint32_t op0 = 0;
+  if (SNAPPY) { // preamble: varint of the uncompressed length
+    uint32_t v = n;
+    do {
+      if (threadIdx.x == 0) out[op0] = uint8_t((v & 0x7fu) | (v >> 7 ? 0x80u : 0u));
+      ++op0;
+      v >>= 7;
+    } while (v);
+  }
+  const uint32_t mflimit = n >= 13 ? n - 12 : 0;        // last match start (inclusive) -- LZ4 block end rules
+  const uint32_t match_end_limit = n >= 5 ? n - 5 : 0;  // matches end before the last 5 bytes
+  if (warp < n_chunks) {
+    uint32_t *tab = tabs + (size_t(warp) << bits);
+    for (uint32_t i = lane; i < (1u << bits); i += 32) tab[i] = kNone;
+    __syncwarp();
+    const uint32_t c0 = warp * cl, c1 = min(n, c0 + cl);
+    const uint32_t start_end = n >= 13 ? min(c1, mflimit + 1) : c0; // match starts: [c0, start_end)
+    const uint32_t mend = min(c1, match_end_limit);                  // match bytes stay below mend (and inside the chunk)
+    uint32_t ip = c0, anchor = c0;
+    bool first = warp != 0;
+    uint32_t op = op0, body_off = op0;
+    LzChunk rec{};
+    while (ip < start_end) {
+      const uint32_t p = ip + lane;
+      const bool in_range = p < start_end && p + 4 <= mend;
       uint32_t seq = 0, cand = kNone;
       if (in_range) {
-        seq = ld4(in + p);
-        uint32_t h = (seq * 2654435761u) >> (32 - kLz4HashBits);
+        seq = ld_u32u(in + p);
+        const uint32_t h = (seq * 2654435761u) >> (32 - bits);
         cand = tab[h];
         tab[h] = p;
       }
-      bool hit = in_range && cand != kNone && cand < p && p - cand <= 65535u && ld4(in + cand) == seq;
-      uint32_t m = __ballot_sync(0xffffffffu, hit);
-      if (!m) {
-        ip += 32;
-        continue;
+      bool hit = in_range && cand != kNone && p - cand <= 65535u && ld_u32u(in + cand) == seq;
+      uint32_t ml = 0;
+      if (hit) { // own extension, 8 bytes per compare
+        const uint32_t lim = min(mend - p, kLzLaneCap);
+        ml = 4;
+        bool open = true;
+        while (open && ml + 8 <= lim) {
+          const uint64_t x = ld_u64u(in + p + ml) ^ ld_u64u(in + cand + ml);
+          if (x) {
+            ml += uint32_t(__ffsll((long long)x) - 1) >> 3;
+            open = false;
+          } else {
+            ml += 8;
+          }
+        }
+        while (open && ml < lim && in[p + ml] == in[cand + ml]) ++ml;
       }
-      uint32_t f = __ffs(m) - 1;
-      uint32_t mp = ip + f, mc = __shfl_sync(0xffffffffu, cand, f);
-      // extend the match 32 bytes at a time
-      uint32_t ml = 4;
-      for (;;) {
-        uint32_t a = mp + ml + lane;
-        bool same = a < match_end_limit && in[a] == in[mc + ml + lane];
-        uint32_t e = __ballot_sync(0xffffffffu, same);
-        uint32_t run = e == 0xffffffffu ? 32 : __ffs(~e) - 1;
-        ml += run;
-        if (run < 32) break;
+      const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+      // ---- take the hits left to right, each one that starts at or after the end of the previous match.  LZ4: the
+      //      walk also hands every taken lane its output position (sequence sizes are uniform arithmetic), the
+      //      lanes then write their sequences side by side.
+      uint32_t cur = ip, sel = 0, my_anchor = 0, my_len = ml, my_q = 0;
+      while (cur - ip < 32) {
+        const uint32_t m = hits & (0xffffffffu << (cur - ip));
+        if (!m) break;
+        const uint32_t f = __ffs(m) - 1;
+        const uint32_t mp = ip + f;
+        uint32_t len = __shfl_sync(0xffffffffu, ml, f);
+        if (len == kLzLaneCap) { // still open: 32 bytes per step
+          const uint32_t mc = __shfl_sync(0xffffffffu, cand, f);
+          for (;;) {
+            const uint32_t a = mp + len + lane;
+            const bool same = a < mend && in[a] == in[mc + len + lane];
+            const uint32_t e = __ballot_sync(0xffffffffu, same);
+            const uint32_t run = e == 0xffffffffu ? 32 : __ffs(~e) - 1;
+            len += run;
+            if (run < 32) break;
+          }
+        }
+        if (first) { // the chunk's first match is emitted by the join phase, behind the previous chunks' tail
+          first = false;
+          rec.has_first = 1, rec.mp1 = mp, rec.mc1 = __shfl_sync(0xffffffffu, cand, f), rec.ml1 = len;
+          const uint32_t lead = mp - c0;
+          body_off = op0 + warp * (cl + lz_slack<SNAPPY>(cl) + 96) + lead + lz_slack<SNAPPY>(lead) + lz_slack<SNAPPY>(len) + 32;
+          op = body_off;
+        } else if constexpr (SNAPPY) { // element sizes depend on (offset, length): written by the warp, one at a time
+          op = snappy_emit_seq(out, op, in + anchor, mp - anchor, mp - __shfl_sync(0xffffffffu, cand, f), len);
+        } else {
+          const uint32_t nl = mp - anchor;
+          if (lane == f) my_anchor = anchor, my_len = len, my_q = op;
+          op += 1 + lz4_len_bytes(nl) + nl + 2 + lz4_len_bytes(len - 4);
+          sel |= 1u << f;
+        }
+        cur = mp + len;
+        anchor = cur;
       }
-      op = SNAPPY ? snappy_emit_seq(out, op, in + anchor, mp - anchor, mp - mc, ml) : lz4_emit_seq(out, op, in + anchor, mp - anchor, mp - mc, ml);
-      ip = mp + ml;
-      anchor = ip;
+      if (!SNAPPY && sel) {
+        const bool mine = (sel >> lane) & 1u;
+        const uint32_t nlit = mine ? p - my_anchor : 0u, mlc = my_len - 4;
+        uint32_t q = my_q, lit_dst = 0;
+        if (mine) {
+          out[q++] = uint8_t((min(nlit, 15u) << 4) | min(mlc, 15u));
+          if (nlit >= 15) {
+            uint32_t r = nlit - 15;
+            for (; r >= 255; r -= 255) out[q++] = 255;
+            out[q++] = uint8_t(r);
+          }
+          lit_dst = q;
+          if (nlit <= 16)
+            for (uint32_t k = 0; k < nlit; ++k) out[q + k] = in[my_anchor + k];
+          q += nlit;
+          const uint32_t offset = p - cand;
+          out[q] = uint8_t(offset), out[q + 1] = uint8_t(offset >> 8);
+          q += 2;
+          if (mlc >= 15) {
+            uint32_t r = mlc - 15;
+            for (; r >= 255; r -= 255) out[q++] = 255;
+            out[q++] = uint8_t(r);
+          }
+        }
+        for (uint32_t big = __ballot_sync(0xffffffffu, mine && nlit > 16); big; big &= big - 1) { // long literal runs: the warp copies
+          const uint32_t f = __ffs(big) - 1;
+          warp_copy(out + __shfl_sync(0xffffffffu, lit_dst, f), in + __shfl_sync(0xffffffffu, my_anchor, f), __shfl_sync(0xffffffffu, nlit, f));
+        }
+      }
+      ip = max(ip + 32, cur);
     }
-    op = SNAPPY ? snappy_emit_seq(out, op, in + anchor, n - anchor, 0, 0) : lz4_emit_seq(out, op, in + anchor, n - anchor, 0, 0);
-    if (lane == 0) cx.bcast[0] = int(op);
+    if (lane == 0) {
+      rec.body_off = body_off, rec.body_len = op - body_off;
+      rec.tail = anchor; // chunk without a match (has_first == 0 on chunks 1..): tail is unused, the run carries on
+      recs[warp] = rec;
+    }
   }
   __syncthreads();
-  uint32_t r = uint32_t(cx.bcast[0]);
+  // ---- join: junction sequences, bodies moved left, final literals
+  uint32_t op = recs[0].body_off + recs[0].body_len, anchor = recs[0].tail;
+  for (uint32_t w = 1; w < n_chunks; ++w) {
+    const LzChunk r = recs[w];
+    if (!r.has_first) continue;
+    op = lz_emit_cta<SNAPPY>(out, op, in + anchor, r.mp1 - anchor, r.mp1 - r.mc1, r.ml1);
+    if (op > r.body_off) cx.flag(SB_PANIC); // the temporary offset is an upper bound of the final one by construction
+    else if (op < r.body_off) {
+      uint8_t *dst = out + op;
+      const uint8_t *src = out + r.body_off;
+      const int64_t len = r.body_len;
+      // 16-byte slots aligned on dst; the regions may overlap (dst < src): load, barrier, store
+      for (int64_t o = -int64_t(uintptr_t(dst) & 15); o < len; o += SB_NT * 16) {
+        const int64_t i = o + int64_t(threadIdx.x) * 16;
+        const bool full = i >= 0 && i + 16 <= len;
+        const int64_t lo = i < 0 ? 0 : i, hi = i + 16 < len ? i + 16 : len; // partial slot: [lo, hi)
+        uint4 v = make_uint4(0, 0, 0, 0);
+        uint8_t edge[16];
+        if (full) v = ld_u128u(src + i);
+        else
+          for (int64_t k = lo; k < hi; ++k) edge[k - lo] = src[k];
+        __syncthreads();
+        if (full) *reinterpret_cast<uint4 *>(dst + i) = v;
+        else
+          for (int64_t k = lo; k < hi; ++k) dst[k] = edge[k - lo];
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    op += r.body_len;
+    anchor = r.tail;
+  }
+  const uint32_t total = lz_emit_cta<SNAPPY>(out, op, in + anchor, n - anchor, 0, 0);
   __syncthreads();
   cx.ar = mark;
-  return r;
+  return total;
 }
 __host__ __device__ __forceinline__ uint64_t lz4_bound(uint64_t n) { return n + n / 255 + 16; }
 
@@ -777,17 +992,34 @@ template <int LEVEL>
 __device__ uint32_t enc_fixed(Dctx &cx, Vals v, int tclass, Bits valid, uint32_t n, EOpts o, uint8_t *out) {
   const int W = v.W;
   const uint32_t tid = threadIdx.x;
+  const Arena entry = cx.ar;
+  if constexpr (LEVEL == 0) {
+    // The page is read by the statistics pass, the distinct table, the samples and the chosen codec (LZ4: by
+    // every probe of the matcher): one copy into shared memory, every later read at shared-memory latency.
+    const uint64_t bytes = uint64_t(n) * W;
+    if (bytes && bytes <= kStageMax && bytes + 16 + kStageKeep <= uint64_t(cx.ar.s_end - cx.ar.s_cur)) { // room for the tables must remain
+      uint8_t *stage = static_cast<uint8_t *>(cx.ar.alloc_shared(bytes + 16));
+      if (stage) {
+        copy_bytes(stage, v.p, bytes);
+        __syncthreads();
+        v.p = stage;
+      }
+    }
+  }
   Arena mark = cx.ar;
   uint8_t *body = out + 9;
 
   // ---- gen_stats (integer/mod.rs:179-229): one pass + the distinct table over ALL slots
   FixedStats st{};
   st.n = n;
-  {
+  // chooser off and nothing forced: the page goes to the default codec, the statistics have no reader
+  const bool need_stats = (o.ratio >= 0 && n) || o.force >= SB_C_RLE;
+  if (need_stats) {
     uint32_t nulls = 0;
     bool sorted = true, neg = false;
     uint64_t mx = 0;
     const uint64_t sign = 1ull << (8 * W - 1);
+#pragma unroll 4
     for (uint32_t i = tid; i < n; i += SB_NT) {
       uint64_t x = v.get(i);
       nulls += !valid.get(i);
@@ -813,12 +1045,12 @@ __device__ uint32_t enc_fixed(Dctx &cx, Vals v, int tclass, Bits valid, uint32_t
   EffFixed raw{v, nullptr, 0};
   HashTab tab{};
   const uint32_t limit = n / 3 + 1;
-  st.unique = n ? hash_distinct(cx, raw, n, limit, &tab, nullptr) : 0;
+  st.unique = !need_stats ? kNone : n ? hash_distinct(cx, raw, n, limit, &tab, nullptr, true) : 0;
   if (*cx.err) return kEncFail;
   st.max_count = 0;
   st.top_first = 0;
   if (st.unique != kNone && n) hash_top(cx, tab, &st.max_count, &st.top_first);
-  cx.ar = mark; // the table is not needed any more (Dict rebuilds over the effective values)
+  // the table stays for now: Dict over a page without nulls reuses it
 
   // ---- choose_compressor (integer/mod.rs:231-308)
   const bool bp_ok = tclass != TC_FLOAT && W == 4 && !st.has_neg && (n % 128 == 0); // bp.rs:93-97
@@ -883,8 +1115,10 @@ __device__ uint32_t enc_fixed(Dctx &cx, Vals v, int tclass, Bits valid, uint32_t
   const bool has_nulls = valid.p && st.null_count;
   uint32_t *src = nullptr;
   uint32_t first_valid = kNone;
+  const bool reuse_tab = codec == SB_C_DICT && !has_nulls && st.unique != kNone; // raw values == effective values
+  if (!reuse_tab) cx.ar = mark;
   if (has_nulls && (codec == SB_C_RLE || codec == SB_C_DICT || codec == SB_C_ONEVALUE)) {
-    src = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
+    src = static_cast<uint32_t *>(cx.ar.alloc_global(uint64_t(n) * 4 + 16));
     if (!src) {
       cx.flag(SB_NYI);
       return kEncFail;
@@ -929,20 +1163,23 @@ __device__ uint32_t enc_fixed(Dctx &cx, Vals v, int tclass, Bits valid, uint32_t
     } else {
       // ids in first-occurrence order over the effective values; leading nulls intern T::default()
       EffFixed acc{v, src, 0};
-      uint32_t *slot_of = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
-      uint32_t *idx = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
+      uint32_t *slot_of = static_cast<uint32_t *>(cx.ar.alloc_global(uint64_t(n) * 4 + 16));
+      uint32_t *idx = static_cast<uint32_t *>(cx.ar.alloc_global(uint64_t(n) * 4 + 16));
       if (!slot_of || !idx) {
         cx.flag(SB_NYI);
         return kEncFail;
       }
-      HashTab dt{};
-      uint32_t k = hash_distinct(cx, acc, n, n + 1, &dt, slot_of);
+      HashTab dt = tab;
+      uint32_t k = st.unique;
+      if (reuse_tab) hash_lookup(acc, n, dt, slot_of);
+      // null replacement only repeats values of the page (or interns T::default()): at most unique + 1 keys
+      else k = hash_distinct(cx, acc, n, st.unique != kNone ? st.unique + 2 : n + 1, &dt, slot_of);
       if (*cx.err || k == kNone) return kEncFail;
       // rank the first occurrences: idx[] is used as the flag / rank array over rows
       for (uint32_t i = tid; i < n; i += SB_NT) idx[i] = 0;
       __syncthreads();
       for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
-        if (dt.rep[h]) idx[dt.first[h]] = 1;
+        if (dt.rep[h]) idx[dt.first(h)] = 1;
       __syncthreads();
       {
         constexpr uint32_t EPT = 8, CH = SB_NT * EPT;
@@ -967,20 +1204,25 @@ __device__ uint32_t enc_fixed(Dctx &cx, Vals v, int tclass, Bits valid, uint32_t
         }
       }
       __syncthreads();
+      uint32_t *ids = slot_of; // rewrite in place: row -> slot -> first row of the key -> its rank
+      for (uint32_t i = tid; i < n; i += SB_NT) ids[i] = idx[dt.first(slot_of[i])];
+      __syncthreads();
+      // the dictionary values are parked in scratch so that the table's shared memory is free for the index page
+      uint8_t *dvals = static_cast<uint8_t *>(cx.ar.alloc_global(uint64_t(k) * W + 16));
+      if (!dvals) {
+        cx.flag(SB_NYI);
+        return kEncFail;
+      }
       for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
-        if (dt.rep[h]) dt.cnt[h] = idx[dt.first[h]]; // slot -> id
+        if (dt.rep[h]) st_le(dvals + uint64_t(idx[dt.first(h)]) * W, acc.key(dt.first(h)), W);
       __syncthreads();
-      uint32_t *ids = slot_of; // rewrite in place: row -> id
-      for (uint32_t i = tid; i < n; i += SB_NT) ids[i] = dt.cnt[slot_of[i]];
-      __syncthreads();
+      cx.ar.s_cur = mark.s_cur;
       EOpts sub = o;
       sub.forbidden |= 1u << SB_C_DICT;
       uint32_t used = enc_fixed<LEVEL + 1>(cx, Vals{reinterpret_cast<const uint8_t *>(ids), 4}, TC_UINT, Bits{nullptr, 0}, n, sub, body);
       if (used == kEncFail) return kEncFail;
       if (tid == 0) st_le(body + used, k, 4);
-      uint8_t *tabo = body + used + 4;
-      for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
-        if (dt.rep[h]) st_le(tabo + uint64_t(dt.cnt[h]) * W, acc.key(dt.first[h]), W);
+      copy_bytes(body + used + 4, dvals, uint64_t(k) * W);
       __syncthreads();
       payload = used + 4 + k * uint32_t(W);
     }
@@ -1004,8 +1246,8 @@ __device__ uint32_t enc_fixed(Dctx &cx, Vals v, int tclass, Bits valid, uint32_t
         }
         top = v.get(st.top_first);
       }
-      uint32_t *rows = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
-      uint8_t *exc = static_cast<uint8_t *>(cx.ar.alloc(uint64_t(n) * W + 16));
+      uint32_t *rows = static_cast<uint32_t *>(cx.ar.alloc_global(uint64_t(n) * 4 + 16));
+      uint8_t *exc = static_cast<uint8_t *>(cx.ar.alloc_global(uint64_t(n) * W + 16));
       if (!rows || !exc) {
         cx.flag(SB_NYI);
         return kEncFail;
@@ -1043,6 +1285,7 @@ __device__ uint32_t enc_fixed(Dctx &cx, Vals v, int tclass, Bits valid, uint32_t
         }
       }
       __syncthreads();
+      cx.ar.s_cur = mark.s_cur; // shared memory back to the exceptions' own page (rows / exc live in scratch)
       if (tid == 0) st_le(body, top, W);
       uint32_t bm = enc_roaring(cx, rows, n_exc, n, body + W + 4);
       if (tid == 0) st_le(body + W, bm, 4);
@@ -1059,7 +1302,7 @@ __device__ uint32_t enc_fixed(Dctx &cx, Vals v, int tclass, Bits valid, uint32_t
   if (payload == kEncFail || *cx.err) return kEncFail;
   put_hdr9(out, codec, payload, n * uint32_t(W)); // uncompressed = n * W (integer/mod.rs:62-63)
   __syncthreads();
-  cx.ar = mark;
+  cx.ar = entry;
   return 9 + payload;
 }
 
@@ -1130,7 +1373,7 @@ __device__ void dict_assign_ids(Dctx &cx, HashTab &dt, uint32_t *slot_of, uint32
   for (uint32_t i = tid; i < n; i += SB_NT) idx[i] = 0;
   __syncthreads();
   for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
-    if (dt.rep[h]) idx[dt.first[h]] = 1;
+    if (dt.rep[h]) idx[dt.first(h)] = 1;
   __syncthreads();
   constexpr uint32_t EPT = 8, CH = SB_NT * EPT;
   uint32_t run = 0;
@@ -1154,7 +1397,7 @@ __device__ void dict_assign_ids(Dctx &cx, HashTab &dt, uint32_t *slot_of, uint32
   }
   __syncthreads();
   for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
-    if (dt.rep[h]) dt.cnt[h] = idx[dt.first[h]];
+    if (dt.rep[h]) dt.cnt[h] = idx[dt.first(h)];
   __syncthreads();
   for (uint32_t i = tid; i < n; i += SB_NT) slot_of[i] = dt.cnt[slot_of[i]];
   __syncthreads();
@@ -1351,7 +1594,7 @@ __device__ uint32_t enc_wide(Dctx &cx, const uint8_t *vals, int W, Bits valid, u
       if (tid == 0) st_le(body + used, k, 4);
       uint8_t *tabo = body + used + 4;
       for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
-        if (dt.rep[h]) acc.put(tabo + uint64_t(dt.cnt[h]) * W, dt.first[h], W);
+        if (dt.rep[h]) acc.put(tabo + uint64_t(dt.cnt[h]) * W, dt.first(h), W);
       __syncthreads();
       payload = used + 4 + k * uint32_t(W);
     }
@@ -1832,7 +2075,7 @@ __device__ uint32_t enc_binary(Dctx &cx, BinView b, Bits valid, uint32_t n, uint
     for (uint32_t i = tid; i < n; i += SB_NT) idx[i] = 0;
     __syncthreads();
     for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
-      if (dt.rep[h]) idx[dt.first[h]] = 1;
+      if (dt.rep[h]) idx[dt.first(h)] = 1;
     __syncthreads();
     {
       constexpr uint32_t EPT = 8, CH = SB_NT * EPT;
@@ -1858,14 +2101,14 @@ __device__ uint32_t enc_binary(Dctx &cx, BinView b, Bits valid, uint32_t n, uint
     }
     __syncthreads();
     for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
-      if (dt.rep[h]) dt.cnt[h] = idx[dt.first[h]];
+      if (dt.rep[h]) dt.cnt[h] = idx[dt.first(h)];
     __syncthreads();
     for (uint32_t i = tid; i < n; i += SB_NT) slot_of[i] = dt.cnt[slot_of[i]]; // row -> id
     __syncthreads();
     // id -> source row of the first occurrence, in id order
     uint32_t *id_row = idx; // idx is free now: rank array consumed
     for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
-      if (dt.rep[h]) id_row[dt.cnt[h]] = acc.row(dt.first[h]);
+      if (dt.rep[h]) id_row[dt.cnt[h]] = acc.row(dt.first(h));
     __syncthreads();
     EOpts sub = o;
     sub.forbidden |= 1u << SB_C_DICT;

@@ -792,7 +792,10 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
       if (m.length > 0xffffffffull || m.num_values > 0xffffffffull) return fail(ctx, SB_OUT_OF_SPEC, "page larger than 4 GiB (u32 size fields)");
       if (m.length + 32 <= stage_cap) {
         n_items += 1;
-        max_stage = std::max<uint32_t>(max_stage, uint32_t(m.length));
+        // a fixed-width page at least as long as its raw values is a plain page or a stored LZ4 block: its value
+        // bytes stream through the ring from global memory, only what precedes them is ever staged
+        const bool raw_sized = fixed_type(ci.leaf.type) && !col_nested(ci) && m.length >= m.num_values * W + 9;
+        max_stage = std::max<uint32_t>(max_stage, uint32_t(raw_sized ? m.length - m.num_values * W : m.length));
         // a page less than half its decoded size is Dict / Freq / RLE coded (binary: any page): give its
         // index buffer (4 bytes per row) room in shared memory instead of the L2 scratch
         if (col_binary(ci) || 2 * m.length < m.num_values * W)
@@ -1039,7 +1042,7 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
     smem_heavy = std::min<uint32_t>(smem, 40 * 1024);
     grid = uint32_t(std::min<uint64_t>(grid, uint64_t(ctx->sm_count) * 2));
   }
-  const uint32_t stage_cap_heavy = split ? smem_heavy - kArenaMin : stage_cap;
+  const uint32_t stage_cap_heavy = smem_heavy - kArenaMin; // what the kernel may stage: its ACTUAL shared memory, not the host's upper bound
   if (n_items) {
     SB_TRY(dev_reserve(ctx, ctx->d_scratch, scratch_per_cta * (uint64_t(grid) + grid_light)));
     SB_TRY_CUDA(cudaMemcpyAsync(dT, hT, tables_bytes, cudaMemcpyHostToDevice, st));
@@ -1052,7 +1055,7 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
     uint32_t grid0 = uint32_t(std::min<uint64_t>(n_plan, uint64_t(ctx->sm_count) * occ));
     sb_decode_kernel<<<grid0, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items0), uint32_t(n_plan),
                                                  d_counters + 4, static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta, d_status,
-                                                 stage_cap, smem, nullptr, d_aux, d_entries, d_counters + 5, 0, 0, nullptr);
+                                                 smem - kArenaMin, smem, nullptr, d_aux, d_entries, d_counters + 5, 0, 0, nullptr);
     SB_TRY_CUDA(cudaGetLastError());
     ctx->stats.kernel_launches += 1;
     SB_TRY_CUDA(cudaMemcpyAsync(h_aux, d_aux, sizeof(PageAux) * n_plan, cudaMemcpyDeviceToHost, st));
