@@ -470,7 +470,7 @@ template <bool SNAPPY> __device__ uint32_t lz_compress_cta(Dctx &cx, const uint8
   const uint32_t match_end_limit = n >= 5 ? n - 5 : 0;  // matches end before the last 5 bytes
   if (warp < n_chunks) {
     uint32_t *tab = tabs + (size_t(warp) << bits);
-    for (uint32_t i = lane; i < (1u << bits); i += 32) tab[i] = kNone;
+    for (uint32_t i = lane; i < (1u << bits); i += 32) tab[i] = 0;
     __syncwarp();
     const uint32_t c0 = warp * cl, c1 = min(n, c0 + cl);
     const uint32_t start_end = n >= 13 ? min(c1, mflimit + 1) : c0; // match starts: [c0, start_end)
@@ -483,11 +483,15 @@ template <bool SNAPPY> __device__ uint32_t lz_compress_cta(Dctx &cx, const uint8
       const uint32_t p = ip + lane;
       const bool in_range = p < start_end && p + 4 <= mend;
       uint32_t seq = 0, cand = kNone;
-      if (in_range) {
-        seq = ld_u32u(in + p);
+      if (in_range) seq = ld_u32u(in + p);
+      {
+        // every lane reads its slot, then the slot takes the LAST position among the lanes with that hash (atomic max
+        // of position + 1, 0 = empty): the table, hence the output, never depends on the order of a warp's stores
         const uint32_t h = (seq * 2654435761u) >> (32 - bits);
-        cand = tab[h];
-        tab[h] = p;
+        if (in_range) cand = tab[h] - 1u; // empty -> kNone
+        __syncwarp();
+        if (in_range) atomicMax(tab + h, p + 1u);
+        __syncwarp();
       }
       bool hit = in_range && cand != kNone && p - cand <= 65535u && ld_u32u(in + cand) == seq;
       uint32_t ml = 0;
