@@ -154,3 +154,34 @@ def test_lz4_own_encoder_chains(ctx):
         assert np.array_equal(ref["values"].view(np.uint8), v.view(np.uint8))
         dec = ctx.batch_read_array(sb.Column(type_, False, enc.data, enc.metas))
         assert_same(dec, ref, type_, False)
+
+
+@pytest.mark.parametrize("codec", [sb.C_LZ4, sb.C_SNAPPY])
+def test_own_matcher_patterns_and_chunk_junctions(ctx, codec):
+    """the CTA-wide matcher of the writer (sb_encode.cuh lz_compress_cta: 4 chunks, parked first matches, junction
+    sequences, bodies moved left): every byte pattern above, at page sizes around the chunking rules (one chunk below
+    2048 bytes per warp, chunk = ceil(n / 4) rounded to 64, pages beyond 64 KiB), is read back to the input by the
+    ORACLE (liblz4 / its Snappy reader) and by the GPU decoder.  A temporary offset below the final one would
+    surface as SB_PANIC, an overlap of two chunk bodies as a wrong byte."""
+    rng = np.random.default_rng(77)
+    sizes = [1, 5, 12, 13, 64, 2047, 2048, 2049, 4096, 8191, 8192, 8193, 8256, 16385, 65535, 65536, 65537, 100003, 262144 + 5]
+    pats = patterns(rng, max(sizes))
+    # stretches that end or start exactly where a chunk does
+    for n in (8192, 65536):
+        cl = n // 4
+        b = bytearray(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+        b[cl - 40:cl + 40] = bytes(80)                       # a match across the first chunk boundary
+        b[2 * cl:2 * cl + 300] = b[2 * cl - 300:2 * cl]      # chunk 2 starts with a copy of chunk 1's tail
+        b[3 * cl + 5:4 * cl] = bytes([7]) * (cl - 5)         # last chunk: 5 literals, then one run to the end
+        pats["junction%d" % n] = bytes(b)
+    for name, buf in pats.items():
+        for n in sizes:
+            if n > len(buf):
+                continue
+            v = np.frombuffer(buf[:n], dtype=np.uint8).copy()
+            enc = ctx.encode_columns([sb.LeafArray(sbo.U8, v)], sb.write_options(codec, None, None))[0]
+            assert len(enc.metas) == 1
+            ref = oracle_decode_column(sbo.U8, False, enc.data, enc.metas)
+            assert np.array_equal(ref["values"], v), (name, n)
+            dec = ctx.batch_read_array(sb.Column(sbo.U8, False, enc.data, enc.metas))
+            assert np.array_equal(dec.values, v), (name, n)
