@@ -1925,7 +1925,7 @@ __device__ uint32_t enc_binary(Dctx &cx, BinView b, Bits valid, uint32_t n, uint
   EffBin raw{b, nullptr};
   HashTab tab{};
   const uint32_t limit = n / 3 + 1;
-  uint32_t unique = n ? hash_distinct(cx, raw, n, limit, &tab, nullptr) : 0;
+  uint32_t unique = n ? hash_distinct(cx, raw, n, limit, &tab, nullptr, true) : 0;
   if (*cx.err) return kEncFail;
   uint32_t max_count = 0, top_first = 0;
   uint64_t total_unique_size = 0;
@@ -2057,9 +2057,10 @@ __device__ uint32_t enc_binary(Dctx &cx, BinView b, Bits valid, uint32_t n, uint
     uint32_t eb = put_entries(cx, b, rows, n_exc, body + 8 + tl + 4 + bm);
     payload = 8 + tl + 4 + bm + eb;
   } else if (codec == SB_C_DICT) { // binary/dict.rs:55-93
+    // the per-row arrays live in scratch so that the table below gets the shared memory
     uint32_t *src = nullptr;
     if (valid.p && nulls) {
-      src = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
+      src = static_cast<uint32_t *>(cx.ar.alloc_global(uint64_t(n) * 4 + 16));
       if (!src) {
         cx.flag(SB_NYI);
         return kEncFail;
@@ -2067,14 +2068,15 @@ __device__ uint32_t enc_binary(Dctx &cx, BinView b, Bits valid, uint32_t n, uint
       fill_forward(cx, valid, n, true, src); // row 0 is interned even when null (:66-74)
     }
     EffBin acc{b, src};
-    uint32_t *slot_of = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
-    uint32_t *idx = static_cast<uint32_t *>(cx.ar.alloc(uint64_t(n) * 4 + 16));
+    uint32_t *slot_of = static_cast<uint32_t *>(cx.ar.alloc_global(uint64_t(n) * 4 + 16));
+    uint32_t *idx = static_cast<uint32_t *>(cx.ar.alloc_global(uint64_t(n) * 4 + 16));
     if (!slot_of || !idx) {
       cx.flag(SB_NYI);
       return kEncFail;
     }
     HashTab dt{};
-    uint32_t k = hash_distinct(cx, acc, n, n + 1, &dt, slot_of);
+    // null replacement only repeats slots of the page: no more keys than the statistics pass counted
+    uint32_t k = hash_distinct(cx, acc, n, unique != kNone ? unique + 2 : n + 1, &dt, slot_of);
     if (*cx.err || k == kNone) return kEncFail;
     for (uint32_t i = tid; i < n; i += SB_NT) idx[i] = 0;
     __syncthreads();
@@ -2114,6 +2116,7 @@ __device__ uint32_t enc_binary(Dctx &cx, BinView b, Bits valid, uint32_t n, uint
     for (uint32_t h = tid; h <= dt.mask; h += SB_NT)
       if (dt.rep[h]) id_row[dt.cnt[h]] = acc.row(dt.first(h));
     __syncthreads();
+    cx.ar.s_cur = mark.s_cur; // the table is done: its shared memory goes to the index page's own statistics
     EOpts sub = o;
     sub.forbidden |= 1u << SB_C_DICT;
     uint32_t used = enc_fixed<1>(cx, Vals{reinterpret_cast<const uint8_t *>(slot_of), 4}, TC_UINT, Bits{nullptr, 0}, n, sub, body);
