@@ -31,7 +31,13 @@ constexpr uint32_t kSmemMin = 40 * 1024;
 constexpr uint32_t kArenaMin = 6 * 1024;     // arena left after the largest staged page
 constexpr uint32_t kTileBytes = 64 * 1024;   // output bytes per work item of an unstaged page
 constexpr uint32_t kTmaChunk = 32 * 1024;
-constexpr uint32_t kBinTile = 32 * 1024;     // plain value bytes per work item of an unstaged binary page
+// plain value bytes per work item of an unstaged binary page.  Measured on plain utf8 pages (16 x 1 M rows, ~78 KB of
+// value bytes per page; tools/ab_utf8.py): 16 KiB 167 us, 32 KiB 118, 64 KiB 108, 128 KiB 94, 256 KiB 95 -- an item costs
+// ~4 us of dependent latency (ticket, descriptors, first TMA round trip) whatever its size.
+#ifndef SB_BIN_TILE
+#define SB_BIN_TILE (128 * 1024)
+#endif
+constexpr uint32_t kBinTile = SB_BIN_TILE;
 
 
 

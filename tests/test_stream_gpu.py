@@ -83,7 +83,7 @@ def strings(rng, n, maxlen, large, nulls=None, minlen=0):
 @pytest.mark.parametrize("type_", [sbo.BINARY, sbo.LARGE_BINARY])
 @pytest.mark.parametrize("default", [sbo.C_NONE, sbo.C_LZ4])
 def test_large_binary_basic_pages(ctx, type_, default):
-    """pages above the staging buffer: tile 0 = validity + offsets, value bytes in 32 KiB slices"""
+    """pages above the staging buffer: tile 0 = validity + offsets, value bytes in 128 KiB slices"""
     rng = np.random.default_rng(14)
     large = type_ == sbo.LARGE_BINARY
     for n, maxlen, page, nulls in ((60_000, 40, 8192, None), (60_000, 40, 8191, 0.3), (200_000, 9, None, None), (50_000, 300, 5000, 0.1),
