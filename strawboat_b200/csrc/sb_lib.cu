@@ -28,6 +28,13 @@ __device__ __forceinline__ bool is_fixed_type(int t) { return (t >= SB_I8 && t <
 constexpr uint32_t kLightSmem = 26 * 1024;   // light kernel: 8 CTAs / SM
 constexpr uint32_t kSmemMax = 74 * 1024;     // dynamic shared memory per CTA: 3 CTAs / SM
 constexpr uint32_t kSmemMin = 40 * 1024;
+#ifndef SB_NEED_EXTRA
+#define SB_NEED_EXTRA (7 * 1024)
+#endif
+// arena wanted next to a compact page and its index buffer (run-start arrays, scan workspaces).  7 KiB: a bit-packed
+// i32 page of 16 KiB + the 32 KiB index allowance of 8192 rows stay at 55 KiB = 4 CTAs per SM (16 KiB made config 2 run
+// at 3: 1256 -> 1202 us, tools/ab_cols.py)
+constexpr uint32_t kNeedExtra = SB_NEED_EXTRA;
 constexpr uint32_t kArenaMin = 6 * 1024;     // arena left after the largest staged page
 constexpr uint32_t kTileBytes = 64 * 1024;   // output bytes per work item of an unstaged page
 constexpr uint32_t kTmaChunk = 32 * 1024;
@@ -805,7 +812,7 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
         // a page less than half its decoded size is Dict / Freq / RLE coded (binary: any page): give its
         // index buffer (4 bytes per row) room in shared memory instead of the L2 scratch
         if (col_binary(ci) || 2 * m.length < m.num_values * W)
-          max_need = std::max<uint64_t>(max_need, m.length + 4 * m.num_values + 16 * 1024);
+          max_need = std::max<uint64_t>(max_need, m.length + 4 * m.num_values + (col_binary(ci) ? 16 * 1024 : kNeedExtra)); // binary: + the entry table
       } else {
         uint64_t out_bytes = ci.leaf.type == SB_BOOL ? (m.num_values + 7) / 8 : m.num_values * W;
         bool tiled = !ci.leaf.nullable && fixed_type(ci.leaf.type) && !col_nested(ci);
