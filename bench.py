@@ -347,7 +347,9 @@ def main():
                     help="who writes the headline's input pages: the oracle writer (reference chooser + liblz4, default) or this library's GPU encoder")
     ap.add_argument("--config3-rows", type=int, default=10_000_000)
     ap.add_argument("--config4-rows", type=int, default=4_000_000)
-    ap.add_argument("--config5-rows", type=int, default=int(os.environ.get("SB_CONFIG5_ROWS", 4_000_000)))
+    ap.add_argument("--config5-rows", type=int, default=int(os.environ.get("SB_CONFIG5_ROWS", 0)),
+                    help="rows of the 64-column table of configs[4] (N > 1); 0 = 12.5 M per GPU, i.e. BASELINE's 100 M rows on 8 GPUs "
+                         "(weak scaling), when the writer rank's host has the memory to frame the file, else 4 M")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -633,7 +635,20 @@ def main():
     if not args.no_extras and world > 1:
         try:
             from strawboat_b200 import parallel
-            res = parallel.bench_config5(ctx, torch, dist, rank, world, args.config5_rows, PAGE_ROWS)
+            rows5 = args.config5_rows
+            if rows5 <= 0:
+                # the writer rank frames the file on the host (body + sink + re-read copy): ~125 bytes per row, 5 copies
+                rows5 = min(100_000_000, 12_500_000 * world)
+                avail = 0
+                try:
+                    avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+                except Exception:
+                    pass
+                flag = torch.tensor([1 if avail >= rows5 * 125 * 8 else 0], device="cuda")
+                dist.broadcast(flag, src=0)
+                if int(flag.item()) == 0:
+                    rows5 = 4_000_000
+            res = parallel.bench_config5(ctx, torch, dist, rank, world, rows5, PAGE_ROWS)
             if rank == 0:
                 line["multi_gpu_encode"] = res
         except Exception as e:
