@@ -10,9 +10,10 @@ from strawboat_b200 import _capi
 ctx0 = sb.Context(0)
 rng = np.random.default_rng(1)
 v = rng.integers(-2**63, 2**63 - 1, 1_000_000, dtype=np.int64)
-enc = ctx0.encode_columns([sb.LeafArray(sb.I64, v)], sb.write_options(sb.C_NONE, None, 8192))[0]
+val = (rng.random(1_000_000) > 0.1) if os.environ.get("NULLABLE") else None
+enc = ctx0.encode_columns([sb.LeafArray(sb.I64, v, validity=val)], sb.write_options(sb.C_NONE, None, 8192))[0]
 tens = [torch.frombuffer(bytearray(enc.data), dtype=torch.uint8).cuda() for _ in range(16)]
-cols = [sb.Column(sb.I64, False, t, enc.metas) for t in tens]
+cols = [sb.Column(sb.I64, val is not None, t, enc.metas) for t in tens]
 ins, keep = ctx0._marshal(cols)
 for name in sys.argv[1:]:
     L = C.CDLL(os.path.join(ROOT, "strawboat_b200", "csrc", name))
