@@ -88,32 +88,58 @@ def gpu_write_columns(ctx, cols, seed, default=None, ratio=2.0):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region.  NVML in-process (nvidia_ml_py) when it loads: spawning
+    `nvidia-smi` every 50 ms from a process with gigabytes of pinned memory stalled the reader threads of the e2e leg
+    for 10-20 ms at a time (steps of 26-30 ms among 10 ms ones); the subprocess form is the fallback."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag, self.reasons = index, [], False, set()
         self.max_mhz = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def sample_nvml(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        self.max_mhz = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = int(get(self.handle))
+        for nm, mask in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)):
+            if bits & mask:
+                self.reasons.add(nm)
+
+    def sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for nm, v in zip(self.NAMES, out[2:]):
+            if "Active" in v and "Not" not in v:
+                self.reasons.add(nm)
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if "Active" in v and "Not" not in v:
-                        self.reasons.add(nm)
+                self.sample_nvml() if self.nvml else self.sample_smi()
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.005 if self.nvml else 0.05)
 
     def result(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "source": "nvml (in-process)" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------- CPU legs
