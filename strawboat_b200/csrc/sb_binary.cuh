@@ -184,7 +184,7 @@ __device__ __forceinline__ bool bin_header(Dctx &cx, const uint8_t *src, uint32_
 // offset; `tab` = this page's slice of the entry table (global).
 // =========================================================================================
 __device__ bool binary_page_size(Dctx &cx, const uint8_t *page, uint32_t page_len, uint32_t vb, uint32_t n, BinEntry *tab,
-                                 uint64_t *out_bytes, uint32_t *val_pos, uint32_t *n_ent) {
+                                 uint64_t *out_bytes, uint32_t *val_pos, uint32_t *n_ent, const PageAux *pre = nullptr) {
   *val_pos = 0;
   *n_ent = 0;
   BinBlock b;
@@ -239,7 +239,17 @@ __device__ bool binary_page_size(Dctx &cx, const uint8_t *page, uint32_t page_le
     }
     uint32_t end;
     uint64_t tot;
-    if (!walk_entries(cx, page, page_len, body_pos + used + 4, k, tab, &end, &tot)) return false;
+    // sb_dict_walk_kernel may have walked this dictionary already (one warp per page, all pages side by side): its
+    // record counts only if it describes the dictionary found here; `tab` then holds the k entries
+    if (pre && pre->pad == 1 && pre->cnt[0] == body_pos + used + 4 && pre->cnt[1] == k) {
+      end = pre->cnt[2];
+      tot = pre->base[0];
+      __syncthreads(); // idx[] complete before the sum below (walk_entries' barrier otherwise)
+    } else if (!walk_entries(cx, page, page_len, body_pos + used + 4, k, tab, &end, &tot)) {
+      return false;
+    }
+    (void)end;
+    (void)tot;
     *n_ent = k;
     uint64_t sum = 0;
     for (uint32_t i = threadIdx.x; i < n; i += SB_NT) {

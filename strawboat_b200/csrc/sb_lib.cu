@@ -185,6 +185,98 @@ __device__ __forceinline__ uint8_t classify_page(const PageDesc &pg, const ColDe
   return 1 | lz_fam;
 }
 
+// ------------------------------------------------------------------------------------
+// Entry walk of binary Dict pages, ahead of the plan pass.  The `[u64 len][bytes]` entries of a dictionary are one
+// serial chain (binary/dict.rs:102-120): ~1000 dependent steps per page of configs[2], on one thread, which made the
+// plan pass rounds x the latency of one page at 3 CTAs per SM.  Here one WARP takes one page (10 per SM), stages the
+// dictionary region in shared memory and walks it, so the chains of a whole column run side by side.  Purely an
+// accelerator: it records (start, k, end, payload total) in the page's PageAux and fills the page's BinEntry slice only
+// when the whole chain parsed cleanly; binary_page_size uses the record only if it describes the dictionary it finds
+// itself, and walks (and reports errors) as before otherwise.
+// ------------------------------------------------------------------------------------
+constexpr uint32_t kWalkWin = 20 * 1024;
+__device__ __forceinline__ uint32_t rd32_bytes(const uint8_t *p) {
+  return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
+}
+__global__ void __launch_bounds__(32)
+    sb_dict_walk_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, const WorkItem *__restrict__ items,
+                        uint32_t n_items, PageAux *aux, BinEntry *entries) {
+  extern __shared__ __align__(16) uint8_t walk_win[]; // kWalkWin + 48
+  const uint32_t lane = threadIdx.x;
+  for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const PageDesc pg = pages[items[it].page];
+    const ColDesc &col = cols[pg.col];
+    if (!(col.type == SB_BINARY || col.type == SB_LARGE_BINARY) || col.n_nested > 1 || pg.aux == 0xffffffffu) continue;
+    const uint8_t *p = pg.src;
+    const uint32_t L = pg.len;
+    uint32_t vb = 0;
+    if (col.nullable) { // validity section: [u32 L][...]
+      if (L < 4) continue;
+      const uint32_t vl = rd32_bytes(p);
+      if (vl > L - 4) continue;
+      vb = 4 + vl;
+    }
+    if (L - vb < 9 + 9 + 4 || p[vb] != SB_C_DICT) continue;
+    if (rd32_bytes(p + vb + 1) > L - vb - 9) continue;
+    const uint32_t body = vb + 9; // index sub-page: hdr9 + its compressed bytes, then [u32 k][entries]
+    const uint64_t used = 9 + uint64_t(rd32_bytes(p + body + 1));
+    if (used + 4 > uint64_t(L - body)) continue;
+    const uint32_t k = rd32_bytes(p + body + uint32_t(used));
+    const uint32_t start = body + uint32_t(used) + 4;
+    if (k < 32 || uint64_t(k) * 8 > uint64_t(L - start)) continue;
+    BinEntry *tab = entries + pg.tab_off;
+    uint32_t pos = start, e = 0;
+    uint64_t sum = 0;
+    bool good = true;
+    while (e < k && good) {
+      // window [pos, pos + wl) of the page, staged at the same 16-byte phase as in global memory
+      const uint32_t wl = min(kWalkWin, L - pos);
+      const uint8_t *g = p + pos;
+      const uint32_t mis = uint32_t(uintptr_t(g) & 15);
+      const uint32_t nvec = (mis + wl + 15) >> 4;
+      const uint4 *gv = reinterpret_cast<const uint4 *>(g - mis);
+      uint4 *sv = reinterpret_cast<uint4 *>(walk_win);
+      for (uint32_t v = lane; v < nvec; v += 32) sv[v] = gv[v];
+      __syncwarp();
+      if (lane == 0) {
+        uint32_t off = 0; // pos - window start
+        for (;;) {
+          if (wl - off < 8) {
+            if (off == 0) good = false; // the page ends inside a header: the plan pass reports it
+            break;                      // else: the header straddles the window end, stage again from here
+          }
+          const uint32_t so = mis + off;
+          const uint32_t *q = reinterpret_cast<const uint32_t *>(walk_win + (so & ~3u));
+          const uint32_t sh = (so & 3) * 8;
+          const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+          const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+          if (hi != 0 || lo > L - pos - 8) {
+            good = false;
+            break;
+          }
+          tab[e] = BinEntry{pos + 8, lo};
+          pos += 8 + lo;
+          off += 8 + lo;
+          sum += lo;
+          if (++e == k || off >= wl) break;
+        }
+      }
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      e = __shfl_sync(0xffffffffu, e, 0);
+      good = __shfl_sync(0xffffffffu, int(good), 0) != 0;
+    }
+    if (good && e == k && lane == 0) {
+      PageAux &ax = aux[pg.aux];
+      ax.cnt[0] = start;
+      ax.cnt[1] = k;
+      ax.cnt[2] = pos;
+      ax.base[0] = sum;
+      ax.pad = 1;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void sb_classify_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, uint32_t n_pages,
                                    Lz4Job *jobs, uint32_t *n_jobs, uint8_t *side_flags, const PageAux *__restrict__ aux, uint32_t light_cap,
                                    uint32_t *n_heavy) {
@@ -445,7 +537,7 @@ __device__ __forceinline__ void decode_body(const PageDesc *__restrict__ pages, 
           if (is_binary_type(col.type)) {
             uint64_t vbytes = 0;
             uint32_t val_pos = 0, n_ent = 0;
-            ok = binary_page_size(cx, p, avail, vb, n, entries + pg.tab_off, &vbytes, &val_pos, &n_ent);
+            ok = binary_page_size(cx, p, avail, vb, n, entries + pg.tab_off, &vbytes, &val_pos, &n_ent, nested ? nullptr : ax);
             ok = !__syncthreads_or(!ok || *cx.err != 0); // per-thread flags (bad dictionary index, ...) count too
             if (tid == 0) {
               ax->value_bytes = ok ? vbytes : 0;
@@ -1066,6 +1158,13 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
   // ---- pass 0 (plan): sizes of binary / nested pages, then the host lays out their outputs
   if (n_plan) {
     uint32_t grid0 = uint32_t(std::min<uint64_t>(n_plan, uint64_t(ctx->sm_count) * occ));
+    if (n_entries) { // flat or nested binary columns present: walk the dictionaries of flat Dict pages, one warp per page
+      const uint32_t gridw = uint32_t(std::min<uint64_t>(n_plan, uint64_t(ctx->sm_count) * 10));
+      sb_dict_walk_kernel<<<gridw, 32, kWalkWin + 48, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items0), uint32_t(n_plan), d_aux,
+                                                           d_entries);
+      SB_TRY_CUDA(cudaGetLastError());
+      ctx->stats.kernel_launches += 1;
+    }
     sb_decode_kernel<<<grid0, SB_NT, smem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items0), uint32_t(n_plan),
                                                  d_counters + 4, static_cast<uint8_t *>(ctx->d_scratch.p), scratch_per_cta, d_status,
                                                  smem - kArenaMin, smem, nullptr, d_aux, d_entries, d_counters + 5, 0, 0, nullptr);
