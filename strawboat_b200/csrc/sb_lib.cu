@@ -236,7 +236,15 @@ __global__ void __launch_bounds__(32)
       const uint32_t nvec = (mis + wl + 15) >> 4;
       const uint4 *gv = reinterpret_cast<const uint4 *>(g - mis);
       uint4 *sv = reinterpret_cast<uint4 *>(walk_win);
-      for (uint32_t v = lane; v < nvec; v += 32) sv[v] = gv[v];
+      for (uint32_t v0 = lane; v0 < nvec; v0 += 32 * 8) { // eight independent 16-byte loads per lane in flight
+        uint4 r[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j)
+          if (v0 + 32 * j < nvec) r[j] = gv[v0 + 32 * j];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j)
+          if (v0 + 32 * j < nvec) sv[v0 + 32 * j] = r[j];
+      }
       __syncwarp();
       if (lane == 0) {
         uint32_t off = 0; // pos - window start
