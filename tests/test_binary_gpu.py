@@ -231,3 +231,75 @@ def test_validity_section_without_bitmap(ctx):
     bad = (0).to_bytes(4, "little") + page[4 + L:]
     res = ctx.decode_columns([sb.Column(sb.I64, True, bad, [(len(bad), 100)])], raise_on_page_error=False)[0]
     assert res.page_status[0] == sb._capi.SB_OUT_OF_SPEC
+
+
+def _table_column(rng, n, table, nulls=0.0, large=False):
+    """n rows drawn from `table` (list of bytes); returns ((offsets, data), validity)"""
+    ids = rng.integers(0, len(table), n)
+    v = (rng.random(n) >= nulls) if nulls else None
+    lens = np.array([len(t) for t in table], dtype=np.int64)[ids]
+    if v is not None:
+        lens = np.where(v, lens, 0)
+    off = np.zeros(n + 1, dtype=np.int64 if large else np.int32)
+    np.cumsum(lens, out=off[1:])
+    parts = [table[i] if (v is None or v[r]) else b"" for r, i in enumerate(ids)]
+    return (off, np.frombuffer(b"".join(parts), np.uint8)), v
+
+
+@pytest.mark.parametrize("type_", [sbo.BINARY, sbo.LARGE_BINARY])
+def test_dict_walk_kernel_windows(ctx, type_):
+    """sb_dict_walk_kernel (one warp per Dict page, dictionary staged in 20 KB windows): dictionaries longer than one
+    window, headers that straddle a window end, one entry longer than a window, empty entries; binary/dict.rs:95-141."""
+    large = type_ == sbo.LARGE_BINARY
+    rng = np.random.default_rng(23)
+    force = sbo.make_opts(force=sbo.C_DICT)
+    # 3000 entries of 0..60 random bytes: ~115 KB of dictionary = 6 windows, arbitrary header phases
+    table = [rng.integers(0, 256, int(l)).astype(np.uint8).tobytes() for l in rng.integers(0, 61, 3000)]
+    table = list(dict.fromkeys(table))
+    vals, _ = _table_column(rng, 6000, table, large=large)
+    roundtrip(ctx, type_, vals, page_size=6000, opts=force, expect_codec="Dict")
+    vals, v = _table_column(rng, 6000, table, nulls=0.3, large=large)
+    roundtrip(ctx, type_, vals, validity=v, page_size=4096, opts=force, expect_codec="Dict")
+    # one 50 KB entry in the middle of 100 short ones (its payload spans three windows), and a 70000-byte one (> u16)
+    table = [b"k%d" % i for i in range(50)] + [bytes(rng.integers(0, 256, 50_000).astype(np.uint8))] + [b"v%03d" % i for i in range(50)] \
+        + [bytes(rng.integers(0, 256, 70_000).astype(np.uint8))]
+    vals, _ = _table_column(rng, 400, table, large=large)
+    roundtrip(ctx, type_, vals, page_size=400, opts=force, expect_codec="Dict")
+    # entry lengths chosen so that headers land on every phase of the 20 KB window end
+    for pad in range(0, 24, 3):
+        table = [b"x" * (997 + pad)] + [b"%05d" % i + b"y" * (i % 7) for i in range(2500)]
+        vals, _ = _table_column(rng, 5000, table, large=large)
+        roundtrip(ctx, type_, vals, page_size=5000, opts=force, expect_codec="Dict")
+
+
+def test_dict_walk_kernel_corrupt_chain(ctx):
+    """a broken `[u64 len]` chain in a dictionary large enough for sb_dict_walk_kernel (k >= 32): the pre-walk leaves no
+    record, the plan pass walks itself and reports the page; the next page is intact"""
+    rng = np.random.default_rng(24)
+    vals, _ = strings(rng, 4096, 300)
+    data, metas = oracle_encode_column(sbo.BINARY, vals, page_size=2048, opts=sbo.make_opts(force=sbo.C_DICT))
+    ctx.decode_columns([sb.Column(sb.BINARY, False, data, metas)])  # healthy call first: stale records in the pools
+    sub_len = 9 + _u32(data, 9 + 1)
+    k = _u32(data, 9 + sub_len)
+    assert k >= 32
+    pos = 9 + sub_len + 4
+    starts = []
+    for _ in range(k):
+        starts.append(pos)
+        pos += 8 + int.from_bytes(data[pos:pos + 8], "little")
+    for e in (0, 40, k - 1):
+        for new_len in (1 << 40, 0xfffffff0, metas[0][0]):
+            bad = bytearray(data)
+            bad[starts[e]:starts[e] + 8] = int(new_len).to_bytes(8, "little")
+            res = ctx.decode_columns([sb.Column(sb.BINARY, False, bytes(bad), metas)], raise_on_page_error=False)[0]
+            assert res.page_status[0] in (sb._capi.SB_OUT_OF_SPEC, sb._capi.SB_IO)
+            _second_page_intact(ctx, res, data, metas)
+    # a shifted but in-bounds length: the chain still parses somewhere; no crash, page 1 untouched
+    bad = bytearray(data)
+    bad[starts[40]:starts[40] + 8] = (1).to_bytes(8, "little") if data[starts[40]] != 1 else (2).to_bytes(8, "little")
+    res = ctx.decode_columns([sb.Column(sb.BINARY, False, bytes(bad), metas)], raise_on_page_error=False)[0]
+    _second_page_intact(ctx, res, data, metas)
+    # the healthy column again: same result as the oracle
+    ref = oracle_decode_column(sbo.BINARY, False, data, metas)
+    dec = ctx.batch_read_array(sb.Column(sb.BINARY, False, data, metas))
+    assert_same(dec, ref, sbo.BINARY, False)
