@@ -188,20 +188,21 @@ __device__ __forceinline__ uint8_t classify_page(const PageDesc &pg, const ColDe
 // ------------------------------------------------------------------------------------
 // Entry walk of binary Dict pages, ahead of the plan pass.  The `[u64 len][bytes]` entries of a dictionary are one
 // serial chain (binary/dict.rs:102-120): ~1000 dependent steps per page of configs[2], on one thread, which made the
-// plan pass rounds x the latency of one page at 3 CTAs per SM.  Here one WARP takes one page (10 per SM), stages the
+// plan pass rounds x the latency of one page at 3 CTAs per SM.  Here one WARP takes one page (12 per SM), stages the
 // dictionary region in shared memory and walks it, so the chains of a whole column run side by side.  Purely an
 // accelerator: it records (start, k, end, payload total) in the page's PageAux and fills the page's BinEntry slice only
 // when the whole chain parsed cleanly; binary_page_size uses the record only if it describes the dictionary it finds
 // itself, and walks (and reports errors) as before otherwise.
 // ------------------------------------------------------------------------------------
-constexpr uint32_t kWalkWin = 20 * 1024;
+constexpr uint32_t kWalkWin = 12 * 1024;                               // bytes of the page staged per window
+constexpr uint32_t kWalkSmem = kWalkWin + 48 + (kWalkWin / 8 + 1) * 4 + 12; // + the header offsets of its entries
 __device__ __forceinline__ uint32_t rd32_bytes(const uint8_t *p) {
   return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
 }
 __global__ void __launch_bounds__(32)
     sb_dict_walk_kernel(const PageDesc *__restrict__ pages, const ColDesc *__restrict__ cols, const WorkItem *__restrict__ items,
                         uint32_t n_items, PageAux *aux, BinEntry *entries) {
-  extern __shared__ __align__(16) uint8_t walk_win[]; // kWalkWin + 48
+  extern __shared__ __align__(16) uint8_t walk_win[]; // kWalkSmem
   const uint32_t lane = threadIdx.x;
   for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
     const PageDesc pg = pages[items[it].page];
@@ -226,8 +227,8 @@ __global__ void __launch_bounds__(32)
     if (k < 32 || uint64_t(k) * 8 > uint64_t(L - start)) continue;
     BinEntry *tab = entries + pg.tab_off;
     uint32_t pos = start, e = 0;
-    uint64_t sum = 0;
     bool good = true;
+    uint32_t *s_off = reinterpret_cast<uint32_t *>(walk_win + kWalkWin + 48); // header offsets of the window's entries (+ end)
     while (e < k && good) {
       // window [pos, pos + wl) of the page, staged at the same 16-byte phase as in global memory
       const uint32_t wl = min(kWalkWin, L - pos);
@@ -246,8 +247,12 @@ __global__ void __launch_bounds__(32)
           if (v0 + 32 * j < nvec) sv[v0 + 32 * j] = r[j];
       }
       __syncwarp();
+      // lane 0 follows the chain through the window and only notes where each header starts (the loop is one
+      // dependent chain on one lane: every instruction in it costs its full latency); the records are written
+      // by all lanes afterwards.  An entry takes at least 8 bytes, so a window holds at most kWalkWin / 8 of them.
+      uint32_t off = 0, c = 0; // off = position - window start, c = entries found in this window
       if (lane == 0) {
-        uint32_t off = 0; // pos - window start
+        const uint32_t cmax = k - e, room = L - pos - 8; // lo <= room - off  <=>  the payload ends inside the page
         for (;;) {
           if (wl - off < 8) {
             if (off == 0) good = false; // the page ends inside a header: the plan pass reports it
@@ -258,27 +263,36 @@ __global__ void __launch_bounds__(32)
           const uint32_t sh = (so & 3) * 8;
           const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
           const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-          if (hi != 0 || lo > L - pos - 8) {
+          if (hi != 0 || lo > room - off) {
             good = false;
             break;
           }
-          tab[e] = BinEntry{pos + 8, lo};
-          pos += 8 + lo;
+          s_off[c] = off;
           off += 8 + lo;
-          sum += lo;
-          if (++e == k || off >= wl) break;
+          if (++c == cmax || off >= wl) break;
         }
+        s_off[c] = off;
       }
-      pos = __shfl_sync(0xffffffffu, pos, 0);
-      e = __shfl_sync(0xffffffffu, e, 0);
+      off = __shfl_sync(0xffffffffu, off, 0);
+      c = __shfl_sync(0xffffffffu, c, 0);
       good = __shfl_sync(0xffffffffu, int(good), 0) != 0;
+      __syncwarp(); // s_off[] written by lane 0 is read by every lane
+      if (good) {
+        for (uint32_t i = lane; i < c; i += 32) {
+          const uint32_t o = s_off[i];
+          tab[e + i] = BinEntry{pos + o + 8, s_off[i + 1] - o - 8};
+        }
+        e += c;
+        pos += off;
+      }
+      __syncwarp();
     }
     if (good && e == k && lane == 0) {
       PageAux &ax = aux[pg.aux];
       ax.cnt[0] = start;
       ax.cnt[1] = k;
       ax.cnt[2] = pos;
-      ax.base[0] = sum;
+      ax.base[0] = uint64_t(pos - start) - 8ull * k; // payload bytes = the chain's span minus its headers
       ax.pad = 1;
     }
     __syncwarp();
@@ -682,6 +696,7 @@ int32_t sb_ctx_create(int32_t device, sb_ctx **out) {
   cudaFuncSetAttribute(sb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemMax));
   cudaFuncSetAttribute(sb_lz4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(sb_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(sb_dict_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100); // 12 one-warp CTAs of 18.5 KB per SM
   *out = ctx;
   return SB_OK;
 }
@@ -1167,8 +1182,8 @@ static int32_t decode_submit(sb_ctx *ctx, const sb_column_in *cols, uint64_t n_c
   if (n_plan) {
     uint32_t grid0 = uint32_t(std::min<uint64_t>(n_plan, uint64_t(ctx->sm_count) * occ));
     if (n_entries) { // flat or nested binary columns present: walk the dictionaries of flat Dict pages, one warp per page
-      const uint32_t gridw = uint32_t(std::min<uint64_t>(n_plan, uint64_t(ctx->sm_count) * 10));
-      sb_dict_walk_kernel<<<gridw, 32, kWalkWin + 48, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items0), uint32_t(n_plan), d_aux,
+      const uint32_t gridw = uint32_t(std::min<uint64_t>(n_plan, uint64_t(ctx->sm_count) * 12));
+      sb_dict_walk_kernel<<<gridw, 32, kWalkSmem, st>>>(d_pages, d_cols, reinterpret_cast<const WorkItem *>(dT + off_items0), uint32_t(n_plan), d_aux,
                                                            d_entries);
       SB_TRY_CUDA(cudaGetLastError());
       ctx->stats.kernel_launches += 1;
