@@ -253,24 +253,25 @@ __global__ void __launch_bounds__(32)
       uint32_t off = 0, c = 0; // off = position - window start, c = entries found in this window
       if (lane == 0) {
         const uint32_t cmax = k - e, room = L - pos - 8; // lo <= room - off  <=>  the payload ends inside the page
-        for (;;) {
-          if (wl - off < 8) {
-            if (off == 0) good = false; // the page ends inside a header: the plan pass reports it
-            break;                      // else: the header straddles the window end, stage again from here
-          }
+        // one loop-carried chain (off -> LDS -> funnel shift -> off) and ONE branch per entry: the exit reasons are
+        // folded into `stop` with selects (a taken-or-not branch per check cost more than the loads)
+        uint32_t stop = 0; // 1 = fewer than 8 bytes of window left, 2 = not a length that fits the page
+        do {
           const uint32_t so = mis + off;
-          const uint32_t *q = reinterpret_cast<const uint32_t *>(walk_win + (so & ~3u));
+          const uint32_t *q = reinterpret_cast<const uint32_t *>(walk_win + (so & ~3u)); // may run into the 48 spare bytes
           const uint32_t sh = (so & 3) * 8;
           const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
           const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-          if (hi != 0 || lo > room - off) {
-            good = false;
-            break;
-          }
+          const bool short_hdr = wl - off < 8;
+          const bool bad = hi != 0 || lo > room - off;
+          stop = short_hdr ? 1u : (bad ? 2u : 0u);
           s_off[c] = off;
-          off += 8 + lo;
-          if (++c == cmax || off >= wl) break;
-        }
+          off += stop ? 0u : 8 + lo;
+          c += stop ? 0u : 1u;
+        } while (stop == 0 && c != cmax && off < wl);
+        // stop == 1 with entries found: the header straddles the window end, stage again from here;
+        // without any: the page ends inside a header -- the plan pass reports it
+        if (stop == 2 || (stop == 1 && c == 0)) good = false;
         s_off[c] = off;
       }
       off = __shfl_sync(0xffffffffu, off, 0);
