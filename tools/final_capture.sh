@@ -1,3 +1,8 @@
+# One gpurun call that re-captures every committed artefact of the headline on the current sources:
+#   GPU test suite, A/B of string pages against a previous build (copy it to strawboat_b200/csrc/libsb_old.so first;
+#   the step just fails without it), ncu --set full capture -> profiles/r2_ncu_traffic.json + summary csv, launch list,
+#   and the default `python bench.py` line.  Everything lands in gpurun_out/final7/; copy what should be judged to profiles/.
+# usage: gpurun --timeout 780 -- 'bash tools/final_capture.sh'
 set -x
 O=gpurun_out/final7; mkdir -p $O
 (timeout 200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4) > $O/pytest.log 2>&1; cat $O/pytest.log
